@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Generate the known-answer fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run ONCE in the dev container, where /root/reference is mounted:
+
+    python tests/golden/generate_golden.py [scenario ...]
+
+The reference ships no golden vectors for the hot path, so these
+are produced by importing `/root/reference/hdpgpc` through the shims in oracle/refshim and
+dumping tensors at the seam functions of SURVEY.md section 8a:
+
+  GPI_model.compute_sq_err_all / log_sq_error / compute_q_lat_all / full_pass_weighted
+  GPI_HDP.compute_snr / weight_mean / LogLik / forward / backward / coupled_state_coef /
+  _safe_exp / cluster_new_batch / compute_q_elbo / full_LDS_elbo / elbo_Linears
+
+"Reference-identical" therefore means identical to the reference code run with this
+container's library versions (torch 2.11, numpy 2.3, scipy 1.18, sklearn 1.9) and with the
+gpytorch hyper-fit replaced by oracle/hyperfit.py (parity unpinned for that sub-step).
+The fixtures travel to the GPU box; the reference does not.
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+
+hdp = refshim.install()
+import torch  # noqa: E402
+from scipy.special import digamma  # noqa: E402
+from hdpgpc.get_data import compute_estimators_LDS  # noqa: E402
+
+DATA_DIR = "/root/reference/hdpgpc/data/mitbih"
+
+
+def npy(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def stack(lst):
+    return np.stack([npy(v) for v in lst]) if len(lst) else np.zeros((0,))
+
+
+def load_record(rec, n, leads, stride=1, start=0):
+    data = np.load(os.path.join(DATA_DIR, rec + ".npy"))[start:start + n][:, ::stride, leads]
+    labels = np.load(os.path.join(DATA_DIR, rec + "_labels.npy"))[start:start + n]
+    return np.ascontiguousarray(data), labels
+
+
+def make_model(data, n_explore_steps=5, free_deg=5, estimation_limit=None, verbose=False):
+    """GPI_HDP with the hyper-parameters of hdpgpc/tests/test_offline.py:37-75."""
+    N, T, L = data.shape
+    with contextlib.redirect_stdout(io.StringIO()):
+        std, std_dif, bound_sigma, bound_gamma = compute_estimators_LDS(data)
+    x_basis = np.atleast_2d(np.arange(0, T, 1, dtype=np.float64)).T
+    x_basis_warp = np.atleast_2d(np.arange(0, T, 2, dtype=np.float64)).T
+    noise_warp = std * 0.1
+    sw = hdp.GPI_HDP(x_basis, x_basis_warp=x_basis_warp, n_outputs=L, kernels=None, model_type='dynamic',
+                     ini_lengthscale=3.0, bound_lengthscale=(1.0, 20.0), ini_gamma=std_dif, ini_sigma=std,
+                     ini_outputscale=300.0, noise_warp=noise_warp, bound_sigma=bound_sigma,
+                     bound_gamma=bound_gamma, bound_noise_warp=(noise_warp * 0.1, noise_warp * 0.2),
+                     warp_updating=False, method_compute_warp='greedy', verbose=verbose, hmm_switch=True,
+                     max_models=100, mode_warp='rough', bayesian_params=True, inducing_points=False,
+                     estimation_limit=estimation_limit,
+                     reestimate_initial_params=True, n_explore_steps=n_explore_steps, free_deg_MNIV=free_deg)
+    x_trains = np.array([x_basis] * N)
+    hyper = dict(std=std, std_dif=std_dif, bound_sigma=np.array(bound_sigma), bound_gamma=np.array(bound_gamma))
+    return sw, x_trains, x_basis, hyper
+
+
+def dump_gp(gp, prefix, out, full=True):
+    """All state of one GPI_model (GPI_model.py:31-73) needed to rebuild it on the device."""
+    out[prefix + "indexes"] = np.asarray(gp.indexes, dtype=np.int64)
+    out[prefix + "N"] = np.int64(gp.N)
+    out[prefix + "fitted"] = np.bool_(gp.fitted)
+    out[prefix + "estimation_limit"] = np.float64(gp.estimation_limit)
+    out[prefix + "x_basis"] = npy(gp.x_basis)
+    out[prefix + "f_star"] = stack(gp.f_star)
+    out[prefix + "f_star_sm"] = stack(gp.f_star_sm)
+    kp = gp.gp.kernel.get_params()
+    out[prefix + "kernel"] = np.array([kp["k1__k1__constant_value"], kp["k1__k2__length_scale"],
+                                       kp["k2__noise_level"]], dtype=np.float64)
+    for name in ["A_def", "Gamma_def", "C_def", "Sigma_def", "ini_cov_def"]:
+        out[prefix + name] = npy(getattr(gp, name))
+    for pname, p in [("int_", gp.internal_params), ("obs_", gp.observation_params)]:
+        out[prefix + pname + "m_mean"] = npy(p.m_mean)
+        out[prefix + pname + "m_r_cov"] = npy(p.m_r_cov)
+        out[prefix + pname + "scale"] = npy(p.scale)
+        out[prefix + pname + "n0"] = np.float64(p.n0)
+    mats = ["cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma"]
+    if full:
+        for name in mats:
+            out[prefix + name] = stack(getattr(gp, name))
+    else:
+        # compact: last matrix + per-step checksums (trace, Frobenius norm, sum)
+        for name in mats:
+            lst = getattr(gp, name)
+            out[prefix + name + "_last"] = npy(lst[-1])
+            out[prefix + name + "_first"] = npy(lst[0])
+            out[prefix + name + "_chk"] = np.array(
+                [[torch.trace(v).item(), torch.linalg.norm(v).item(), torch.sum(v).item()] for v in lst])
+            out[prefix + name + "_len"] = np.int64(len(lst))
+
+
+def hmm_block(sw, q, snr, prefix, out, use_saved_snr=False):
+    """HMM smoothing exactly as GPI_HDP.cluster_new_batch (GPI_HDP.py:2987-3001) /
+    estimate_q_all (:2856-2862) run it."""
+    M = q.shape[1]
+    transTheta, startTheta = sw.transTheta, sw.startTheta
+    dsum = digamma(torch.sum(transTheta[:M, :M + 1], axis=1) + 1e-5)
+    transPi = digamma(transTheta[:M, :M]) - dsum[:, None]
+    startPi = digamma(startTheta[:M]) - digamma(torch.sum(startTheta[:M + 1]) + 1e-5)
+    qbar = sw.weight_mean(q, None if use_saved_snr else snr)
+    q_norm, _ = sw.LogLik(qbar)
+    alpha, margprob = sw.forward(startPi, transPi, q_norm)
+    beta = sw.backward(transPi, q_norm, margprob)
+    logresp, _ = sw.LogLik(torch.log(alpha * beta), axis=1)
+    logpair = sw.coupled_state_coef(alpha, beta, transPi, q_norm, margprob)
+    logrespPair, _ = sw.LogLik(logpair, axis=1)
+    resp = sw._safe_exp(logresp)
+    respPair = sw._safe_exp(logrespPair)
+    out[prefix + "startPi"] = npy(startPi)
+    out[prefix + "transPi"] = npy(transPi)
+    out[prefix + "trans_A"] = npy(sw.compute_trans_A(M))
+    out[prefix + "qbar"] = npy(qbar)
+    out[prefix + "q_norm"] = npy(q_norm)
+    out[prefix + "alpha"] = npy(alpha)
+    out[prefix + "margprob"] = npy(margprob)
+    out[prefix + "beta"] = npy(beta)
+    out[prefix + "z"] = npy(torch.argmax(resp, dim=1)).astype(np.int32)
+    out[prefix + "zpair"] = npy(torch.argmax(respPair.reshape(respPair.shape[0], -1), dim=1)).astype(np.int32)
+    out[prefix + "respPair_dtype"] = str(respPair.dtype)
+    out[prefix + "startStateCount"] = npy(resp[0])
+    out[prefix + "transStateCount"] = npy(torch.sum(respPair, axis=0))
+    out[prefix + "Nm"] = npy(torch.sum(resp, dim=0))
+    out[prefix + "Q_em"] = npy(torch.sum(qbar[torch.where(resp == 1.0)]))
+    return resp, respPair, qbar
+
+
+def offline_scenario(name, rec, n, leads, stride, n_new, full, n_explore_steps=5):
+    t0 = time.time()
+    data, labels = load_record(rec, n, leads, stride)
+    new, new_labels = load_record(rec, n_new, leads, stride, start=n)
+    sw, x_trains, x_basis, hyper = make_model(data, n_explore_steps=n_explore_steps)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        sw.include_batch(x_trains, data)
+    log = buf.getvalue()
+    N, T, L = data.shape
+    M = sw.M
+    out = dict(data=data, labels=labels.astype("U1"), new=new, new_labels=new_labels.astype("U1"),
+               x_basis=x_basis, M=np.int64(M), L=np.int64(L))
+    for k, v in hyper.items():
+        out["hyper_" + k] = np.asarray(v)
+    out["resp_assigned"] = np.stack([npy(r) for r in sw.resp_assigned])
+    out["train_elbo"] = np.array([float(e) for e in sw.train_elbo])
+    out["transTheta"] = npy(sw.transTheta)
+    out["startTheta"] = npy(sw.startTheta)
+    out["rho"] = npy(sw.rho)
+    out["omega"] = npy(sw.omega)
+    out["hdp_hyp"] = np.array([sw.gamma, sw.transAlpha, sw.startAlpha, sw.kappa])
+    out["snr_norm"] = npy(sw.snr_norm)
+    out["q_last"] = npy(sw.q_last)
+    out["q_lat_last"] = npy(sw.q_lat_last)
+    out["snr_last"] = npy(sw.snr_last)
+    out["resp_last"] = npy(sw.resp_last)
+    out["kernel_def"] = np.array([sw.kernel_def.get_params()[k] for k in
+                                  ["k1__k1__constant_value", "k1__k2__length_scale", "k2__noise_level"]])
+    out["kernel_def_noise_bounds"] = np.array(sw.kernel_def.k2.noise_level_bounds)
+    out["ini_sigma_def"] = np.float64(sw.ini_sigma_def)
+    out["ini_gamma_def"] = np.float64(sw.ini_gamma_def)
+    out["free_deg_MNIV"] = np.float64(sw.free_deg_MNIV)
+
+    xt = torch.from_numpy(x_trains)
+    yt = torch.from_numpy(data)
+    xn = torch.from_numpy(np.array([x_basis] * n_new))
+    yn = torch.from_numpy(new)
+    q_all = torch.zeros(N, M, L)
+    q_all_nofirst = torch.zeros(N, M, L)
+    q_lat_all = torch.zeros(N, M, L)
+    snr_all = torch.zeros(N, M, L)
+    q_new = torch.zeros(n_new, M, L)
+    snr_new = torch.zeros(n_new, M, L)
+    lds_lik = np.zeros((L, M))
+    with contextlib.redirect_stdout(io.StringIO()):
+        for ld in range(L):
+            for m in range(M):
+                gp = sw.gpmodels[ld][m]
+                dump_gp(gp, f"gp_{ld}_{m}_", out, full=full)
+                q_all[:, m, ld] = gp.compute_sq_err_all(xt, yt[:, :, [ld]])
+                q_all_nofirst[:, m, ld] = gp.compute_sq_err_all(xt, yt[:, :, [ld]], no_first=True)
+                q_lat_all[:, m, ld] = gp.compute_q_lat_all(xt)
+                snr_all[:, m, ld] = sw.compute_snr(yt[:, :, ld], gp)
+                for i in range(n_new):
+                    q_new[i, m, ld] = gp.log_sq_error(xn[i], yn[i, :, [ld]], i=-1)
+                snr_new[:, m, ld] = sw.compute_snr(yn[:, :, ld], gp)
+                lds_lik[ld, m] = float(gp.return_LDS_param_likelihood())
+    out["q_all"] = npy(q_all)
+    out["q_all_nofirst"] = npy(q_all_nofirst)
+    out["q_lat_all"] = npy(q_lat_all)
+    out["snr_all"] = npy(snr_all)
+    out["q_new"] = npy(q_new)
+    out["snr_new"] = npy(snr_new)
+    out["lds_param_lik"] = lds_lik
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        resp, respPair, qbar = hmm_block(sw, q_all, snr_all, "train_", out)
+        hmm_block(sw, q_new, snr_new, "new_", out)
+        hmm_block(sw, q_all, snr_all, "saved_", out, use_saved_snr=True)
+        labels_new = sw.cluster_new_batch(np.array([x_basis] * n_new), new)
+        out["new_cluster_new_batch"] = npy(labels_new).astype(np.int32)
+        # ELBO pieces (GPI_HDP.py:1796-1864, :1025-1074, :2682-2700)
+        qlat_bar = sw.weight_mean(q_lat_all, snr_all)
+        q_bas, elbo_bas = sw.compute_q_elbo(resp, respPair, qbar, qlat_bar, sw.gpmodels, M, snr=snr_all,
+                                            post=False, verb=False)
+        out["elbo_q_bas"] = npy(q_bas)
+        out["elbo_bas"] = npy(elbo_bas)
+        out["elbo_Q_lat"] = npy(torch.sum(qlat_bar[torch.where(resp == 1.0)]))
+        out["elbo_linears"] = np.float64(sw.elbo_Linears(resp, respPair))
+        out["elbo_full_LDS"] = np.array([float(sw.full_LDS_elbo(sw.gpmodels[ld], torch.sum(resp, dim=0)))
+                                         for ld in range(L)])
+        out["elbo_nonlinear"] = np.float64(sw.calcELBO_NonlinearTerms(resp=npy(resp), respPair=npy(respPair)))
+
+        # Fresh-chain replays (GPI_model.full_pass_weighted :377-406) for every final cluster, lead 0:
+        # fresh default GP -> hyper-fit on first member -> Kalman/pair-smoother/MNIW per member ->
+        # full RTS pass -> scores.  Pins SURVEY section 8a rows a5-a10, a1, a4.
+        z = npy(torch.argmax(resp, dim=1))
+        for m in range(min(M, 3)):
+            gp = sw.create_gp_default()
+            rcol = torch.from_numpy((z == m).astype(np.float64))
+            qc, qlc = gp.full_pass_weighted(xt, yt[:, :, [0]], rcol)
+            dump_gp(gp, f"chain_{m}_", out, full=full)
+            out[f"chain_{m}_resp"] = npy(rcol)
+            out[f"chain_{m}_q"] = npy(qc)
+            out[f"chain_{m}_q_lat"] = npy(qlc)
+            out[f"chain_{m}_snr"] = npy(sw.compute_snr(yt[:, :, 0], gp))
+    out["n_chain"] = np.int64(min(M, 3))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    with open(os.path.join(HERE, name + ".log.txt"), "w") as fh:
+        fh.write("\n".join(log.splitlines()[-60:]))
+    print(f"{name}: M={M} sizes={npy(torch.sum(resp, dim=0)).astype(int).tolist()} "
+          f"elbo={out['train_elbo'][-1]:.4f} -> {os.path.getsize(path) / 1e6:.2f} MB in {time.time() - t0:.0f}s")
+
+
+def hmm_synth():
+    """Random (q, snr, transTheta, startTheta) through the reference HMM code; K=2..7, L=1..3."""
+    rng = np.random.default_rng(20261018)
+    out = {}
+    cases = [(200, 3, 2), (300, 6, 1), (257, 2, 3), (500, 7, 2), (64, 4, 1)]
+    out["n_cases"] = np.int64(len(cases))
+    data = np.zeros((4, 8, 1))
+    for c, (N, K, L) in enumerate(cases):
+        sw, _, _, _ = make_model(np.random.default_rng(1).normal(size=(6, 8, L)) * 50.0)
+        sw.M = K
+        # sticky-ish random Dirichlet pseudo-counts, (K+1)x(K+1) as in _calcThetaFull (:400-422)
+        tt = rng.gamma(1.0, 1.0, size=(K + 1, K + 1)) + np.eye(K + 1) * rng.uniform(0, 20)
+        if c == 2:
+            tt[0, 1] = 1e-9  # exercise the tiny-probability floors (:3584, :3643)
+        st = rng.gamma(1.0, 1.0, size=(K + 1,))
+        sw.transTheta = torch.from_numpy(tt)
+        sw.startTheta = torch.from_numpy(st)
+        lab = np.zeros(N, dtype=int)
+        for t in range(1, N):
+            lab[t] = lab[t - 1] if rng.uniform() < 0.85 else rng.integers(K)
+        q = rng.normal(size=(N, K, L)) * 3.0 - 120.0
+        q[np.arange(N), lab, :] += rng.uniform(0.5, 12.0, size=(N, 1))
+        if c == 3:
+            q[10:20] -= 5000.0  # far-away beats: exp underflow in safe_exp
+        snr = rng.normal(size=(N, K, L)) * 4.0
+        out[f"c{c}_q"] = q
+        out[f"c{c}_snr"] = snr
+        out[f"c{c}_transTheta"] = tt
+        out[f"c{c}_startTheta"] = st
+        with contextlib.redirect_stdout(io.StringIO()):
+            hmm_block(sw, torch.from_numpy(q), torch.from_numpy(snr), f"c{c}_", out)
+    path = os.path.join(HERE, "hmm_synth.npz")
+    np.savez_compressed(path, **out)
+    print(f"hmm_synth -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def inducing():
+    """Emission score on a grid different from the basis grid: GPI_model.log_sq_error ->
+    observe -> IterativeGaussianProcess.pred_dist kernel branch (GPI.py:470-501)."""
+    data, _ = load_record("100", 24, [0], 3)
+    N, T, L = data.shape
+    sw, x_trains, x_basis, hyper = make_model(data)
+    out = dict(data=data, x_basis=x_basis)
+    xt = torch.from_numpy(x_trains)
+    yt = torch.from_numpy(data)
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp = sw.create_gp_default()
+        resp = torch.zeros(N)
+        resp[[0, 2, 3, 5, 8, 9, 13, 14, 20]] = 1.0
+        gp.full_pass_weighted(xt, yt[:, :, [0]], resp)
+        dump_gp(gp, "gp_", out, full=True)
+        rng = np.random.default_rng(7)
+        x_off = x_basis + rng.uniform(-0.3, 0.3, size=x_basis.shape)
+        x_sub = x_basis[::2] + 0.25
+        res_off, res_sub, res_last = [], [], []
+        mu_cov = {}
+        for i in [1, 4, 9]:
+            f, c = gp.observe(torch.from_numpy(x_off), i)
+            mu_cov[f"obs_off_{i}_mean"] = npy(f)
+            mu_cov[f"obs_off_{i}_cov"] = npy(c)
+            for n in range(6):
+                res_off.append(float(gp.log_sq_error(torch.from_numpy(x_off), yt[n, :, [0]], i=i)))
+        for n in range(6):
+            res_last.append(float(gp.log_sq_error(torch.from_numpy(x_off), yt[n, :, [0]], i=-1)))
+        f, c = gp.observe(torch.from_numpy(x_sub), 3)
+        mu_cov["obs_sub_3_mean"] = npy(f)
+        mu_cov["obs_sub_3_cov"] = npy(c)
+        for n in range(6):
+            res_sub.append(float(gp.log_sq_error(torch.from_numpy(x_sub), yt[n, ::2, [0]], i=3)))
+        # constant-diagonal Sigma short-cut (GPI.py:497-498): the untouched prior state 0 of a fresh GP
+        gp0 = sw.create_gp_default()
+        f, c = gp0.observe(torch.from_numpy(x_off), 0)
+        mu_cov["obs_prior_mean"] = npy(f)
+        mu_cov["obs_prior_cov"] = npy(c)
+    out.update(mu_cov)
+    out["x_off"] = x_off
+    out["x_sub"] = x_sub
+    out["score_off"] = np.array(res_off).reshape(3, 6)
+    out["score_off_last"] = np.array(res_last)
+    out["score_sub"] = np.array(res_sub)
+    path = os.path.join(HERE, "inducing_T30.npz")
+    np.savez_compressed(path, **out)
+    print(f"inducing_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+SCENARIOS = {
+    # full state dumps at T=30 (every 3rd sample of the bundled T=90 beats keeps fixtures small)
+    "offline_rec100_T30_L1": lambda: offline_scenario("offline_rec100_T30_L1", "100", 40, [0], 3, 24, True),
+    "offline_rec102_T30_L2": lambda: offline_scenario("offline_rec102_T30_L2", "102", 48, [0, 1], 3, 24, True, 3),
+    # the shipped shape (T=90, lead 0, test_offline.py settings); compact dump (checksums + last states)
+    "offline_rec100_T90_L1": lambda: offline_scenario("offline_rec100_T90_L1", "100", 40, [0], 1, 24, False),
+    "hmm_synth": hmm_synth,
+    "inducing_T30": inducing,
+}
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    names = sys.argv[1:] or list(SCENARIOS)
+    for nm in names:
+        SCENARIOS[nm]()
