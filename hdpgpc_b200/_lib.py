@@ -1,0 +1,80 @@
+"""ctypes binding of include/hdpgpc_b200.h.  No CPU fallback: a missing library is an error."""
+import ctypes
+import os
+
+from .build import LIBPATH
+
+_c = ctypes
+_p = _c.c_void_p
+_i64 = _c.c_int64
+_int = _c.c_int
+_dbl = _c.c_double
+
+# name -> (restype, argtypes); must list every symbol declared in include/hdpgpc_b200.h
+PROTOTYPES = {
+    "hgp_version": (_int, []),
+    "hgp_build_info": (_c.c_char_p, []),
+    "hgp_last_error": (_c.c_char_p, []),
+    "hgp_launch_count": (_i64, []),
+    "hgp_pack_leads": (_int, [_p, _i64, _int, _int, _p, _p]),
+    "hgp_chol_batched": (_int, [_p, _i64, _int, _p, _dbl, _p, _p, _p, _p]),
+    "hgp_tri_inverse_batched": (_int, [_p, _i64, _int, _p, _p]),
+    "hgp_packed_factor_bytes": (_i64, [_int]),
+    "hgp_pack_factors": (_int, [_p, _i64, _int, _p, _p]),
+    "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p]),
+    "hgp_score_pairs": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _i64, _p, _p]),
+    "hgp_snr_states": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p]),
+    "hgp_lead_weights": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p]),
+    "hgp_hmm_workspace_bytes": (_i64, [_i64, _int]),
+    "hgp_hmm_smooth": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p, _p, _i64,
+                              _c.POINTER(_int), _p]),
+    "hgp_suffstats_workspace_bytes": (_i64, [_i64, _int]),
+    "hgp_suffstats": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _i64, _p]),
+    "hgp_emission_means": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
+}
+
+
+class HgpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libhdpgpc_b200.so (building is the job of __graft_entry__.build / hdpgpc_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise HgpError(f"{LIBPATH} is missing: run `python -m hdpgpc_b200.build` (needs nvcc). "
+                       "hdpgpc_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIBPATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().hgp_last_error().decode()
+        raise HgpError(f"{what} failed (rc={rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise HgpError("hdpgpc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,284 @@
+// Batched SPD factorisation, triangular inverse and operand packing (sm_100a).
+//
+// chol_batched restates GPI_model._chol_spd (reference GPI_model.py:83-87) for a batch of
+// T x T float64 matrices, one CTA per matrix, blocked right-looking with the current panel in
+// shared memory and the trailing matrix in L2.  tri_inverse_batched produces W = L^{-1} so the
+// Mahalanobis term becomes a single triangular product (see include/hdpgpc_b200.h).
+#include "hgp_common.cuh"
+
+namespace {
+
+constexpr int NB = 16;           // panel width
+constexpr int CHOL_THREADS = 256;
+
+__global__ void pack_leads_kernel(const double* __restrict__ Y, int64_t N, int T, int L, double* __restrict__ out) {
+    int64_t total = N * (int64_t)T * L;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // i indexes the output [L][N][T]
+        int64_t t = i % T;
+        int64_t n = (i / T) % N;
+        int64_t ld = i / ((int64_t)T * N);
+        out[i] = Y[(n * T + t) * L + ld];
+    }
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS)
+chol_kernel(const double* __restrict__ Sigma, int T, const double* __restrict__ add_diag, double jitter_scale,
+            double* __restrict__ Lfac, double* __restrict__ logdet, int* __restrict__ info) {
+    extern __shared__ double smem[];
+    double* Dk = smem;                       // [NB][NB+1]
+    double* P = smem + NB * (NB + 1);        // [T][NB+1]
+    __shared__ double s_red[CHOL_THREADS / 32];
+    __shared__ double s_jit;
+    __shared__ int s_info;
+
+    const int64_t f = blockIdx.x;
+    const double* S = Sigma + f * (int64_t)T * T;
+    double* A = Lfac + f * (int64_t)T * T;
+    const int tid = threadIdx.x;
+    const double add = add_diag ? add_diag[f] : 0.0;
+
+    // diag mean of (S + add I)
+    double part = 0.0;
+    for (int i = tid; i < T; i += CHOL_THREADS) part += fabs(S[(int64_t)i * T + i] + add);
+    part = warp_sum(part);
+    if ((tid & 31) == 0) s_red[tid >> 5] = part;
+    if (tid == 0) s_info = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < CHOL_THREADS / 32; ++w) tot += s_red[w];
+        s_jit = jitter_scale * fmax(tot / T, HGP_EPS);
+    }
+    __syncthreads();
+    const double jit = s_jit;
+    for (int idx = tid; idx < T * T; idx += CHOL_THREADS) {
+        int i = idx / T, j = idx % T;
+        double v;
+        if (j > i) v = 0.0;
+        else if (j == i) v = (S[idx] + add) + jit;   // sym() leaves the diagonal unchanged
+        else v = 0.5 * (S[idx] + S[(int64_t)j * T + i]);
+        A[idx] = v;
+    }
+    __syncthreads();
+
+    double ld_acc = 0.0;
+    for (int k0 = 0; k0 < T; k0 += NB) {
+        const int nb = min(NB, T - k0);
+        // diagonal block -> shared
+        for (int idx = tid; idx < nb * nb; idx += CHOL_THREADS) {
+            int i = idx / nb, j = idx % nb;
+            Dk[i * (NB + 1) + j] = A[(int64_t)(k0 + i) * T + k0 + j];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            for (int j = 0; j < nb; ++j) {
+                double d = Dk[j * (NB + 1) + j];
+                if (!(d > 0.0) && tid == 0 && s_info == 0) s_info = k0 + j + 1;
+                double s = sqrt(d);
+                __syncwarp();
+                if (tid == 0) Dk[j * (NB + 1) + j] = s;
+                if (tid > j && tid < nb) Dk[tid * (NB + 1) + j] /= s;
+                __syncwarp();
+                if (tid > j && tid < nb) {
+                    double lij = Dk[tid * (NB + 1) + j];
+                    for (int c = j + 1; c <= tid; ++c) Dk[tid * (NB + 1) + c] -= lij * Dk[c * (NB + 1) + j];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nb * nb; idx += CHOL_THREADS) {
+            int i = idx / nb, j = idx % nb;
+            if (j <= i) A[(int64_t)(k0 + i) * T + k0 + j] = Dk[i * (NB + 1) + j];
+        }
+        if (tid == 0) for (int j = 0; j < nb; ++j) ld_acc += log(Dk[j * (NB + 1) + j]);
+        const int r0 = k0 + nb;      // first trailing row
+        const int nt = T - r0;
+        // panel solve: X L_kk^T = A[r0:, k0:k0+nb], one thread per row
+        for (int r = tid; r < nt; r += CHOL_THREADS) {
+            double x[NB];
+            double* arow = A + (int64_t)(r0 + r) * T + k0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c < nb) {
+                    double v = arow[c];
+                    for (int p = 0; p < c; ++p) v -= x[p] * Dk[c * (NB + 1) + p];
+                    x[c] = v / Dk[c * (NB + 1) + c];
+                    arow[c] = x[c];
+                    P[r * (NB + 1) + c] = x[c];
+                }
+            }
+        }
+        __syncthreads();
+        // trailing update (lower part only): A[i][j] -= P[i] . P[j]
+        const int ty = tid >> 4, tx = tid & 15;
+        for (int ib = 0; ib < nt; ib += 16) {
+            int i = ib + ty;
+            for (int jb = 0; jb <= ib; jb += 16) {
+                int j = jb + tx;
+                if (i < nt && j <= i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NB; ++c)
+                        if (c < nb) acc += P[i * (NB + 1) + c] * P[j * (NB + 1) + c];
+                    A[(int64_t)(r0 + i) * T + r0 + j] -= acc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (logdet) logdet[f] = 2.0 * ld_acc;
+        info[f] = s_info;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ Wout) {
+    extern __shared__ double smem[];
+    double* Lii = smem;                      // [NB][NB+1]
+    double* Inv = Lii + NB * (NB + 1);       // [NB][NB+1]
+    double* R = Inv + NB * (NB + 1);         // [nblk][NB][NB+1]
+    const int64_t f = blockIdx.x;
+    const double* Lm = Lfac + f * (int64_t)T * T;
+    double* W = Wout + f * (int64_t)T * T;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int nblk = (T + NB - 1) / NB;
+
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int r0 = bi * NB;
+        const int nb = min(NB, T - r0);
+        // zero the strict upper part of this block row (columns > r0+row)
+        for (int idx = tid; idx < nb * T; idx += 256) {
+            int i = idx / T, j = idx % T;
+            if (j > r0 + i) W[(int64_t)(r0 + i) * T + j] = 0.0;
+        }
+        if (ty < nb && tx < nb) Lii[ty * (NB + 1) + tx] = Lm[(int64_t)(r0 + ty) * T + r0 + tx];
+        __syncthreads();
+        // Inv = Lii^{-1}: thread c solves column c
+        if (tid < nb) {
+            const int c = tid;
+            double x[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (i < nb) {
+                    if (i < c) x[i] = 0.0;
+                    else if (i == c) x[i] = 1.0 / Lii[i * (NB + 1) + i];
+                    else {
+                        double v = 0.0;
+                        for (int p = c; p < i; ++p) v += Lii[i * (NB + 1) + p] * x[p];
+                        x[i] = -v / Lii[i * (NB + 1) + i];
+                    }
+                    Inv[i * (NB + 1) + c] = x[i];
+                }
+            }
+        }
+        // R[bj] = sum_{k in [c0, r0)} L[r0+ty][k] * W[k][c0+tx]
+        for (int bj = 0; bj < bi; ++bj) {
+            const int c0 = bj * NB;
+            double acc = 0.0;
+            if (ty < nb) {
+                const double* lrow = Lm + (int64_t)(r0 + ty) * T;
+                for (int k = c0; k < r0; ++k) acc += lrow[k] * W[(int64_t)k * T + c0 + tx];
+            }
+            R[(bj * NB + ty) * (NB + 1) + tx] = acc;
+        }
+        __syncthreads();
+        for (int bj = 0; bj < bi; ++bj) {
+            const int c0 = bj * NB;
+            if (ty < nb) {
+                double acc = 0.0;
+                for (int p = 0; p <= ty; ++p) acc += Inv[ty * (NB + 1) + p] * R[(bj * NB + p) * (NB + 1) + tx];
+                W[(int64_t)(r0 + ty) * T + c0 + tx] = -acc;
+            }
+        }
+        if (ty < nb && tx < nb && tx <= ty) W[(int64_t)(r0 + ty) * T + r0 + tx] = Inv[ty * (NB + 1) + tx];
+        __syncthreads();
+    }
+}
+
+// Packed factor stream for hgp_score_tiles.  Tp = T rounded up to 8, nrb = Tp/8 row blocks.
+// chunk kc (k columns [8kc, 8kc+8)) holds row blocks rb = kc..nrb-1; block (kc, rb) is 32 lanes x 2
+// doubles: element (lane, ks) = W[8 rb + lane/4][8 kc + 4 ks + lane%4], i.e. the A fragments of two
+// consecutive DMMA.8x8x4 k-steps, so one LDS.128 per lane feeds two tensor-core instructions.
+__global__ void pack_factors_kernel(const double* __restrict__ W, int T, int nrb, int64_t packed_doubles,
+                                    double* __restrict__ out) {
+    const int64_t f = blockIdx.y;
+    const double* Wf = W + f * (int64_t)T * T;
+    double* o = out + f * packed_doubles;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < packed_doubles;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        // locate chunk: offset(kc) = 64 * (kc*nrb - kc(kc-1)/2)
+        int64_t blk = idx / 64;                 // global (kc, rb) block index
+        int within = (int)(idx % 64);
+        int kc = 0;
+        // small linear search (nrb <= 32)
+        int64_t base = 0;
+        while (blk >= base + (nrb - kc)) { base += nrb - kc; ++kc; }
+        int rb = kc + (int)(blk - base);
+        int lane = within >> 1, ks = within & 1;
+        int row = 8 * rb + (lane >> 2);
+        int col = 8 * kc + 4 * ks + (lane & 3);
+        double v = 0.0;
+        if (row < T && col < T && col <= row) v = Wf[(int64_t)row * T + col];
+        o[idx] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" int hgp_pack_leads(const double* Y_ntl, int64_t N, int T, int L, double* Y_lnt, void* stream) {
+    HGP_REQUIRE(N >= 0 && T > 0 && L > 0, "hgp_pack_leads: bad sizes");
+    if (N == 0) return 0;
+    int64_t total = N * (int64_t)T * L;
+    int blocks = (int)hgp_min64((total + 255) / 256, 148 * 16);
+    pack_leads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y_ntl, N, T, L, Y_lnt);
+    HGP_LAUNCH_CHECK("hgp_pack_leads");
+    return 0;
+}
+
+extern "C" int hgp_chol_batched(const double* Sigma, int64_t F, int T, const double* add_diag, double jitter_scale,
+                                double* Lfac, double* logdet, int* info, void* stream) {
+    HGP_REQUIRE(F >= 0 && T > 0 && T <= 1024, "hgp_chol_batched: need 0 < T <= 1024");
+    if (F == 0) return 0;
+    size_t smem = sizeof(double) * (NB * (NB + 1) + (size_t)T * (NB + 1));
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_chol_batched: smem attribute");
+    }
+    chol_kernel<<<(unsigned)F, CHOL_THREADS, smem, (cudaStream_t)stream>>>(Sigma, T, add_diag, jitter_scale, Lfac, logdet, info);
+    HGP_LAUNCH_CHECK("hgp_chol_batched");
+    return 0;
+}
+
+extern "C" int hgp_tri_inverse_batched(const double* Lfac, int64_t F, int T, double* W, void* stream) {
+    HGP_REQUIRE(F >= 0 && T > 0 && T <= 1024, "hgp_tri_inverse_batched: need 0 < T <= 1024");
+    if (F == 0) return 0;
+    int nblk = (T + NB - 1) / NB;
+    size_t smem = sizeof(double) * (size_t)(2 + nblk) * NB * (NB + 1);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_tri_inverse_batched: smem attribute");
+    }
+    tri_inverse_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(Lfac, T, W);
+    HGP_LAUNCH_CHECK("hgp_tri_inverse_batched");
+    return 0;
+}
+
+extern "C" int64_t hgp_packed_factor_bytes(int T) {
+    int64_t nrb = (T + 7) / 8;
+    return 512 * (nrb * (nrb + 1) / 2);
+}
+
+extern "C" int hgp_pack_factors(const double* W, int64_t F, int T, double* Wpacked, void* stream) {
+    HGP_REQUIRE(F >= 0 && T > 0 && T <= 256, "hgp_pack_factors: need 0 < T <= 256");
+    if (F == 0) return 0;
+    int nrb = (T + 7) / 8;
+    int64_t pd = hgp_packed_factor_bytes(T) / 8;
+    dim3 grid((unsigned)hgp_min64((pd + 255) / 256, 64), (unsigned)F);
+    pack_factors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, T, nrb, pd, Wpacked);
+    HGP_LAUNCH_CHECK("hgp_pack_factors");
+    return 0;
+}

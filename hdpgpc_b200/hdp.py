@@ -1,0 +1,384 @@
+"""E-step surface of the reference's `GPI_HDP` (reference hdpgpc/GPI_HDP.py) on the device:
+lead weighting, HMM smoothing, hard responsibilities, sufficient statistics, and the
+`cluster_new_batch(learning=False)` entry point -- same method names and argument meaning.
+
+`EStepEngine` is the struct-of-arrays form of one E-step sweep: it owns the
+device tables and runs score -> SNR -> lead weights -> HMM -> arg-max -> statistics for a beat
+slice; `EStepEngine.sweep()` is what bench.py times.  Beats shard by contiguous time slice over
+ranks (`torch.distributed`, NCCL): cluster tables are broadcast, the HMM boundary messages are
+all-gathered, the statistics all-reduced.
+"""
+import numpy as np
+import torch
+from scipy.special import digamma
+
+from . import ops
+from ._lib import HgpError
+from .model import GPI_model, snr_state_index, state_index_map
+
+F64 = torch.float64
+I32 = torch.int32
+
+
+# ------------------------------------------------------------------------------------------
+# host-side K-sized operands, restated from the reference (these are O(K^2) scalars)
+# ------------------------------------------------------------------------------------------
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float64)
+
+
+def _safe_exp_rows(x):
+    with np.errstate(invalid="ignore", over="ignore"):
+        e = np.exp(x - np.max(x, axis=1, keepdims=True))
+    return np.nan_to_num(e, nan=1e-8)
+
+
+def compute_trans_A(transTheta, K):
+    """GPI_HDP.compute_trans_A (GPI_HDP.py:3527-3535)."""
+    tt = _np(transTheta)
+    tp = digamma(tt[:K, :K]) - digamma(np.sum(tt[:K, :K + 1], axis=1))[:, None]
+    if tp.shape[0] == K:
+        return tp
+    out = np.full((K, K), -np.inf)
+    out[:K - 1, :K - 1] = tp
+    return out
+
+
+def expected_log_pi(transTheta, startTheta, M):
+    """startPi / transPi of cluster_new_batch(learning=False) (GPI_HDP.py:2989-2993)."""
+    tt, st = _np(transTheta), _np(startTheta)
+    transPi = digamma(tt[:M, :M]) - digamma(np.sum(tt[:M, :M + 1], axis=1) + 1e-5)[:, None]
+    startPi = digamma(st[:M]) - digamma(np.sum(st[:M + 1]) + 1e-5)
+    return startPi, transPi
+
+
+def hmm_operands(transTheta, startPi, K):
+    """pi, PiT (forward, GPI_HDP.py:3574-3585), Pi (backward, :3637-3643), Pc (pair coefficient,
+    :3686-3687, no floor).  PiT is NOT Pi transposed: different max-shifts and floors."""
+    sp = _np(startPi)
+    pi = np.full(K, -np.inf)
+    pi[:min(K, sp.shape[0])] = sp[:K]
+    pi = np.exp(pi)
+    tA = compute_trans_A(transTheta, K)
+    PiT = _safe_exp_rows(tA.T.copy())
+    PiT[PiT < 1e-6] += 1e-4
+    pi[pi < 1e-10] += 1e-4
+    Pc = _safe_exp_rows(tA.copy())
+    Pi = Pc.copy()
+    Pi[Pi < 1e-5] += 1e-4
+    return pi, PiT, Pi, Pc
+
+
+# ------------------------------------------------------------------------------------------
+# struct-of-arrays E-step
+# ------------------------------------------------------------------------------------------
+class LeadTables:
+    """Everything one lead needs on the device for a sweep over its beat slice."""
+
+    def __init__(self, Y, mu, W, state_of, factor_of_state, mu_sm, snr_state_of, tile_path=None):
+        self.Y = Y                                  # [N, T]
+        self.mu = mu                                # [S, T]   emission means C_i f_i
+        self.W = W                                  # [F, T, T] whitening factors L^{-1}
+        self.state_of = state_of                    # [N, M] int32 (-1: cluster empty)
+        self.factor_of_state = factor_of_state      # [S] int32
+        self.mu_sm = mu_sm                          # [S2, T]  smoothed latent means (SNR)
+        self.snr_state_of = snr_state_of            # [N, M] int32 or None (use_snr False)
+        N, T = Y.shape
+        M = state_of.shape[1]
+        self.N, self.T, self.M = N, T, M
+        self.Wpacked = None
+        self.factor_of_cluster = None
+        self.pair_n = self.pair_m = None
+        self.use_tiles = False
+        if tile_path is None:
+            tile_path = T <= 256
+        if tile_path and N > 0:
+            self._plan_tiles()
+
+    def _plan_tiles(self):
+        """Main factor per cluster = the factor most of its beats use; the rest go to the pair kernel."""
+        f_of = self.factor_of_state.long()[self.state_of.clamp_min(0).long()]        # [N, M]
+        f_of = torch.where(self.state_of >= 0, f_of, torch.full_like(f_of, -1))
+        main = torch.mode(f_of, dim=0).values                                          # [M]
+        # a column whose mode is -1 (empty cluster) scores 0 everywhere; any factor index will do
+        main_c = main.clamp_min(0)
+        exc = (f_of != main_c.unsqueeze(0)) & (f_of >= 0)
+        n_exc = int(exc.sum())
+        if n_exc * 2 > self.N * self.M:
+            return  # mostly per-state covariances (estimation_limit=None regime): pair kernel for everything
+        self.use_tiles = True
+        self.factor_of_cluster = main_c.to(I32).contiguous()
+        self.Wpacked = ops.pack_factors(self.W)
+        if n_exc:
+            nz = torch.nonzero(exc)
+            self.pair_n = nz[:, 0].to(I32).contiguous()
+            self.pair_m = nz[:, 1].to(I32).contiguous()
+
+    def score(self, out):
+        if self.use_tiles:
+            ops.score_tiles(self.Y, self.mu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out)
+            if self.pair_n is not None:
+                ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m,
+                                out=out)
+        else:
+            ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, out=out)
+        return out
+
+    def snr(self, out):
+        return ops.snr_states(self.Y, self.mu_sm, self.snr_state_of, out=out)
+
+
+class EStepEngine:
+    """One E-step sweep over a (slice of a) beat sequence:  q[N,M,L] -> lead weights -> q-bar ->
+    HMM forward/backward -> arg-max resp / respPair -> N_m, startStateCount, transStateCount, Q_em
+    (= reference cluster_new_batch(learning=False), GPI_HDP.py:2975-3001, + the count lines :890-892)."""
+
+    def __init__(self, leads, transTheta, startTheta, lead_w=None, group=None):
+        self.leads = leads
+        self.L = len(leads)
+        self.N, self.M = leads[0].N, leads[0].M
+        self.device = leads[0].Y.device
+        self.group = group
+        self.rank, self.world = 0, 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.rank = torch.distributed.get_rank(group)
+            self.world = torch.distributed.get_world_size(group)
+        self.lead_w = lead_w
+        self.use_snr = leads[0].snr_state_of is not None
+        if not self.use_snr and lead_w is None:
+            self.lead_w = torch.full((self.N, self.L), 1.0 / self.L, dtype=F64, device=self.device)
+        self.set_hdp(transTheta, startTheta)
+        dev = self.device
+        self.q = torch.zeros((self.L, self.N, self.M), dtype=F64, device=dev)
+        self.snr = torch.zeros((self.L, self.N, self.M), dtype=F64, device=dev) if self.use_snr else None
+        self._hmm_ws = torch.empty(ops._lib.load().hgp_hmm_workspace_bytes(max(self.N, 1), self.M), dtype=torch.uint8,
+                                   device=dev)
+        self._stat_ws = torch.empty(ops._lib.load().hgp_suffstats_workspace_bytes(self.N, self.M), dtype=torch.uint8,
+                                    device=dev)
+        self.hmm_rounds = 0
+        self.boundary_rounds = 0
+
+    def set_hdp(self, transTheta, startTheta):
+        M = self.M
+        startPi, _ = expected_log_pi(transTheta, startTheta, M)
+        pi, PiT, Pi, Pc = hmm_operands(transTheta, startPi, M)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        self.pi, self.PiT, self.Pi, self.Pc = up(pi), up(PiT), up(Pi), up(Pc)
+
+    # -- pieces --
+    def score_all(self):
+        for ld, tb in enumerate(self.leads):
+            tb.score(self.q[ld])
+            if self.use_snr:
+                tb.snr(self.snr[ld])
+        return self.q, self.snr
+
+    def responsibilities(self):
+        qbar, e, w, flags = ops.lead_weights(self.q, self.snr if self.use_snr else None, self.lead_w)
+        if self.world == 1:
+            hm = ops.hmm_smooth(e, self.pi, self.PiT, self.Pi, self.Pc, workspace=self._hmm_ws)
+            self.boundary_rounds = 0
+        else:
+            hm = self._hmm_sharded(e)
+        self.hmm_rounds = hm.rounds
+        return qbar, e, w, hm
+
+    def _hmm_sharded(self, e):
+        """Exact HMM smoothing over rank-sharded beats: every rank scans its slice from a guessed
+        boundary, the boundary messages (2K doubles per rank) are all-gathered, and slices whose
+        incoming message changed are re-scanned; repeat until no boundary moves (bitwise)."""
+        dist = torch.distributed
+        K = self.M
+        G, r = self.world, self.rank
+        has_prev, has_next = r > 0, r < G - 1
+        bin_ = torch.empty(2 * K, dtype=F64, device=self.device)
+        bin_[:K] = 1.0 / K                     # guess for alpha of the previous rank's last beat
+        bin_[K:] = 1.0                         # guess for (beta . e) of the next rank's first beat
+        gathered = torch.empty((G, 2 * K), dtype=F64, device=self.device)
+        hm = None
+        rounds = 0
+        while True:
+            hm = ops.hmm_smooth(e, self.pi, self.PiT, self.Pi, self.Pc, boundary_in=bin_, has_prev=has_prev,
+                                has_next=has_next, workspace=self._hmm_ws)
+            dist.all_gather_into_tensor(gathered, hm.boundary_out, group=self.group)
+            new_in = bin_.clone()
+            if has_prev:
+                new_in[:K] = gathered[r - 1, :K]
+            if has_next:
+                new_in[K:] = gathered[r + 1, K:]
+            changed = (new_in.view(torch.int64) != bin_.view(torch.int64)).any().to(torch.int32)
+            dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=self.group)
+            rounds += 1
+            if int(changed) == 0:
+                break
+            bin_ = new_in
+            if rounds > G + 2:
+                raise HgpError("sharded HMM boundary exchange did not converge")
+        self.boundary_rounds = rounds
+        return hm
+
+    def statistics(self, qbar, hm):
+        Nm, trans, start, Qem, packed = ops.suffstats(hm.z, hm.zpair, qbar, is_first_slice=(self.rank == 0),
+                                                      workspace=self._stat_ws)
+        if self.world > 1:
+            torch.distributed.all_reduce(packed, group=self.group)
+        return dict(Nm=Nm, transStateCount=trans, startStateCount=start, Q_em=Qem, packed=packed)
+
+    def sweep(self):
+        self.score_all()
+        qbar, e, w, hm = self.responsibilities()
+        st = self.statistics(qbar, hm)
+        st.update(qbar=qbar, e=e, w=w, z=hm.z, zpair=hm.zpair, alpha=hm.alpha, beta=hm.beta, marg=hm.marg)
+        return st
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's method surface
+# ------------------------------------------------------------------------------------------
+class GPI_HDP:
+    """E-step methods of the reference GPI_HDP operating on device-resident models.
+
+    gpmodels[ld][m] are hdpgpc_b200.GPI_model objects (e.g. GPI_model.from_reference(ref_gp))."""
+
+    def __init__(self, gpmodels, transTheta, startTheta, snr_norm=None, use_snr=True, device="cuda"):
+        self.gpmodels = gpmodels
+        self.n_outputs = len(gpmodels)
+        self.M = len(gpmodels[0])
+        self.transTheta = _np(transTheta)
+        self.startTheta = _np(startTheta)
+        self.use_snr = use_snr
+        self.device = torch.device(device)
+        self.snr_norm = None if snr_norm is None else self._t(snr_norm)
+        self.last_engine = None
+
+    def _t(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=F64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
+
+    # ---- GPI_HDP.compute_snr (GPI_HDP.py:732-748) ----
+    def compute_snr(self, y_trains, gp):
+        Y = self._t(y_trains)
+        if Y.dim() == 3:
+            Y = Y[:, :, 0].contiguous()
+        N = Y.shape[0]
+        if not self.use_snr:
+            return torch.ones(N, dtype=F64, device=self.device)
+        j = snr_state_index(gp.indexes, gp.f_star_sm.shape[0], N).astype(np.int32).reshape(N, 1)
+        return ops.snr_states(Y, gp.f_star_sm, torch.from_numpy(j).to(self.device))[:, 0]
+
+    # ---- GPI_HDP.weight_mean (:685-701), 3-D q (N, M, L) ----
+    def weight_mean(self, q, snr=None):
+        q = self._t(q)
+        q_lnm = q.permute(2, 0, 1).contiguous()
+        if snr is None:
+            qbar, _, _, _ = ops.lead_weights(q_lnm, None, self.snr_norm)
+        else:
+            qbar, _, _, _ = ops.lead_weights(q_lnm, self._t(snr).permute(2, 0, 1).contiguous(), None)
+        return qbar
+
+    # ---- GPI_HDP.LogLik (:632-661), axis=1 ----
+    def LogLik(self, logSoftEv, axis=1):
+        x = self._t(logSoftEv)
+        c = torch.max(x, dim=axis)[0]
+        if torch.any(torch.isinf(c)):
+            return x, c
+        return x - c.unsqueeze(axis), c
+
+    def _operands(self, pi, K):
+        pi_, PiT, Pi, Pc = hmm_operands(self.transTheta, _np(pi), K)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        return up(pi_), up(PiT), up(Pi), up(Pc)
+
+    def _smooth(self, pi, q):
+        q = self._t(q)
+        N, K = q.shape
+        _, e, _, _ = ops.lead_weights(q.reshape(1, N, K), None, torch.ones((N, 1), dtype=F64, device=self.device))
+        pi_, PiT, Pi, Pc = self._operands(pi, K)
+        return ops.hmm_smooth(e, pi_, PiT, Pi, Pc)
+
+    # ---- forward / backward / coupled_state_coef (:3546-3699).  trans_A is ignored exactly as the
+    #      reference ignores it (recomputed from self.transTheta, :3580, :3637, :3686) ----
+    def forward(self, pi=None, trans_A=None, q=None):
+        hm = self._smooth(pi, q)
+        self._last = (q, hm)
+        return hm.alpha, hm.marg
+
+    def backward(self, trans_A=None, q=None, margprob=None):
+        if getattr(self, "_last", None) is not None and self._last[0] is q:
+            return self._last[1].beta
+        startPi, _ = expected_log_pi(self.transTheta, self.startTheta, q.shape[1])
+        return self._smooth(startPi, q).beta
+
+    def hard_assignments(self, pi, q):
+        """(z, zpair): arg-max indices of _safe_exp(logresp) and _safe_exp(logrespPair) (:338-350)."""
+        hm = self._smooth(pi, q)
+        return hm.z, hm.zpair
+
+    def _safe_exp(self, x):
+        """GPI_HDP._safe_exp (:338-350): one-hot of the row arg-max (float64 for 2-D, float32 for 3-D)."""
+        x = self._t(x)
+        if x.dim() == 2:
+            y = torch.zeros_like(x)
+            y.scatter_(-1, x.argmax(dim=-1, keepdim=True), 1.0)
+            return y
+        N = x.shape[0]
+        xf = x.reshape(N, -1)
+        y = torch.zeros_like(xf, dtype=torch.float32)
+        y.scatter_(1, xf.argmax(dim=-1, keepdim=True), 1.0)
+        return y.reshape_as(x)
+
+    # ---- build the struct-of-arrays tables for a batch scored against LAST states (i = -1) or
+    #      against the time-indexed states of the training sequence ----
+    def build_engine(self, y_trains, mode="last"):
+        Y = self._t(y_trains)
+        N, T, L = Y.shape
+        if L != self.n_outputs:
+            raise HgpError("y_trains has a different number of leads than the model")
+        Yp = ops.pack_leads(Y)
+        leads = []
+        for ld in range(L):
+            mus, Ws, fos, mus_sm = [], [], [], []
+            s_off = f_off = sm_off = 0
+            state_of = np.full((N, self.M), -1, dtype=np.int32)
+            snr_of = np.zeros((N, self.M), dtype=np.int32)
+            for m, gp in enumerate(self.gpmodels[ld]):
+                tb = gp.tables()
+                nS = tb["mu"].shape[0]
+                mu_m = tb["mu"]
+                fos_m = tb["factor_of_state"].copy()
+                if mode == "last":
+                    # log_sq_error(x, y, i=-1): last state; an empty cluster scores against its prior state 0
+                    state_of[:, m] = s_off + (nS - 1)
+                else:
+                    if gp.N > 0:
+                        i_vals, first = state_index_map(gp.indexes, N)
+                        mu_m = torch.cat([mu_m, mu_m[1:2]], dim=0)
+                        fos_m = np.concatenate([fos_m, [tb["first_factor"]]]).astype(np.int32)
+                        state_of[:, m] = s_off + np.where(first, nS, i_vals)
+                mus.append(mu_m)
+                fos.append(fos_m + f_off)
+                Ws.append(tb["W"])
+                mus_sm.append(gp.f_star_sm)
+                snr_of[:, m] = sm_off + snr_state_index(gp.indexes, gp.f_star_sm.shape[0], N)
+                s_off += mu_m.shape[0]
+                f_off += tb["W"].shape[0]
+                sm_off += gp.f_star_sm.shape[0]
+            dev = self.device
+            leads.append(LeadTables(Yp[ld], torch.cat(mus), torch.cat(Ws), torch.from_numpy(state_of).to(dev),
+                                    torch.from_numpy(np.concatenate(fos).astype(np.int32)).to(dev),
+                                    torch.cat(mus_sm), torch.from_numpy(snr_of).to(dev) if self.use_snr else None))
+        eng = EStepEngine(leads, self.transTheta, self.startTheta)
+        self.last_engine = eng
+        return eng
+
+    # ---- GPI_HDP.cluster_new_batch(learning=False) (:2975-3001) ----
+    def cluster_new_batch(self, x_trains, y_trains, learning=False, it_limit=None, warp=False):
+        if learning or warp:
+            raise HgpError("cluster_new_batch(learning=True / warp=True) is outside the built hot path")
+        for gp in self.gpmodels[0]:
+            gp._check_grid(x_trains)
+        eng = self.build_engine(y_trains, mode="last")
+        out = eng.sweep()
+        self.last_sweep = out
+        return out["z"].long()

@@ -1,0 +1,205 @@
+"""Device-resident mirror of the reference's per-(cluster, lead) model `GPI_model`
+(reference hdpgpc/GPI_model.py:16) for the E-step seam: same method names, argument meaning and
+return types (torch float64 tensors), state held as struct-of-arrays on the GPU instead of Python
+lists of T x T tensors.  Index logic (which historical state scores which beat) is host-side
+integer work; all floating-point arithmetic runs in the CUDA library.
+"""
+from bisect import bisect_right
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import HgpError
+
+F64 = torch.float64
+
+
+class LinAlgError(HgpError):
+    """Raised where the reference would raise torch.linalg.LinAlgError (non-SPD covariance)."""
+
+
+def _stack(lst, device):
+    if isinstance(lst, torch.Tensor):
+        return lst.to(device=device, dtype=F64).contiguous()
+    if isinstance(lst, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(lst, dtype=np.float64)).to(device)
+    arrs = [v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v) for v in lst]
+    return torch.from_numpy(np.ascontiguousarray(np.stack(arrs), dtype=np.float64)).to(device)
+
+
+def _vecs(lst, device):
+    t = _stack(lst, device)
+    if t.dim() == 3:  # reference carries (T, 1) column vectors
+        t = t[:, :, 0].contiguous()
+    return t
+
+
+def state_index_map(indexes, n_samps, no_first=False):
+    """i_vals / first_mask of GPI_model.compute_sq_err_all (GPI_model.py:497-513)."""
+    idx = np.asarray(indexes, dtype=np.int64)
+    pos = np.full(n_samps, -1, dtype=np.int64)
+    pos[idx] = np.arange(idx.size)
+    exact = pos >= 0
+    closest = np.maximum(np.searchsorted(idx, np.arange(n_samps), side="right") - 1, 0)
+    i_vals = np.where(exact, pos + 1, np.maximum(closest, 1))
+    first = exact & (i_vals == 1) & (not no_first)
+    return i_vals, first
+
+
+def snr_state_index(indexes, n_states, n_samps):
+    """j of GPI_HDP.compute_snr (GPI_HDP.py:739): clip(find_closest_lower(t), 1, len(f_star_sm) - 1)."""
+    idx = np.asarray(indexes, dtype=np.int64)
+    p = np.searchsorted(idx, np.arange(n_samps), side="right")
+    j = np.where(p > 0, p - 1, 0)
+    return np.minimum(np.maximum(j, 1), n_states - 1)
+
+
+class GPI_model:
+    def __init__(self, x_basis, f_star, f_star_sm, C, Sigma, indexes, estimation_limit=None,
+                 A=None, Gamma=None, cov_f_sm=None, device="cuda"):
+        self.device = torch.device(device)
+        self.x_basis = np.asarray(x_basis, dtype=np.float64).reshape(-1)
+        self.T = self.x_basis.shape[0]
+        self.f_star = _vecs(f_star, self.device)          # [nF, T] filtered means (observe uses these)
+        self.f_star_sm = _vecs(f_star_sm, self.device)    # [nF, T] smoothed means (SNR, q_lat)
+        self.C = _stack(C, self.device)                   # [nC, T, T]
+        self.Sigma = _stack(Sigma, self.device)           # [nC, T, T]
+        self.A = None if A is None else _stack(A, self.device)
+        self.Gamma = None if Gamma is None else _stack(Gamma, self.device)
+        self.cov_f_sm = None if cov_f_sm is None else _stack(cov_f_sm, self.device)
+        self.indexes = [int(i) for i in indexes]
+        self.N = len(self.indexes)
+        self.estimation_limit = np.inf if estimation_limit is None else estimation_limit
+        self._tables = None
+
+    # ---- construction helpers ----
+    @classmethod
+    def from_reference(cls, gp, device="cuda"):
+        """gp: a reference GPI_model (or any object with the same list attributes)."""
+        return cls(gp.x_basis, gp.f_star, gp.f_star_sm, gp.C, gp.Sigma, gp.indexes,
+                   estimation_limit=getattr(gp, "estimation_limit", None), A=gp.A, Gamma=gp.Gamma,
+                   cov_f_sm=gp.cov_f_sm, device=device)
+
+    @classmethod
+    def from_dump(cls, z, prefix, device="cuda"):
+        """From a tests/golden fixture written by generate_golden.dump_gp(full=True)."""
+        g = lambda k: z[prefix + k]
+        return cls(g("x_basis"), g("f_star"), g("f_star_sm"), g("C"), g("Sigma"), g("indexes"),
+                   estimation_limit=float(g("estimation_limit")), A=g("A"), Gamma=g("Gamma"),
+                   cov_f_sm=g("cov_f_sm"), device=device)
+
+    # ---- index rules (host integer work) ----
+    def find_closest_lower(self, t):
+        """GPI_model.find_closest_lower (GPI_model.py:584-593)."""
+        idx = bisect_right(self.indexes, t)
+        return idx - 1 if idx else 0
+
+    def param_index(self, t):
+        """Which (C, Sigma) a state index uses: GPI_model.observe (:626-662) + get_params (:664-669)."""
+        nC = self.C.shape[0]
+        nF = self.f_star.shape[0]
+        if self.N == 0:
+            return 0, 0
+        if t < 0:
+            t = nF + t
+            return (t if t < nC else nC - 1), t   # python negative indexing of both lists
+        if self.N <= t:
+            return nC - 1, nF - 1
+        if self.estimation_limit <= t:
+            return nC - 1, t
+        return (t if t < nC else nC - 1), t
+
+    def tables(self):
+        """Emission-mean table and whitening factors for every state (cached; states are immutable
+        between chain updates).  Factor F-1 is the `first`-jitter variant of state 1 (GPI_model.py:527-529)."""
+        if self._tables is not None:
+            return self._tables
+        nF = self.f_star.shape[0]
+        cidx = np.zeros(nF, dtype=np.int32)
+        fidx = np.zeros(nF, dtype=np.int32)
+        for t in range(nF):
+            c, f = self.param_index(t)
+            cidx[t], fidx[t] = c, f
+        dev = self.device
+        mu = ops.emission_means(self.C, self.f_star, torch.from_numpy(cidx).to(dev), torch.from_numpy(fidx).to(dev))
+        uniq, inv = np.unique(cidx, return_inverse=True)
+        n_u = len(uniq)
+        sig = self.Sigma.index_select(0, torch.from_numpy(uniq.astype(np.int64)).to(dev))
+        add = torch.zeros(n_u + 1, dtype=F64, device=dev)
+        first_state = min(1, nF - 1)
+        sig = torch.cat([sig, self.Sigma[int(cidx[first_state])].unsqueeze(0)], dim=0)
+        add[n_u] = 1e-2 * torch.mean(torch.diagonal(self.Sigma[0]))
+        Lf, info = ops.chol_batched(sig, add_diag=add)
+        W = ops.tri_inverse_batched(Lf)
+        bad = torch.nonzero(info).flatten()
+        if bad.numel():
+            raise LinAlgError(f"linalg.cholesky: factor {int(bad[0])} is not positive-definite "
+                              f"(leading minor {int(info[bad[0]])})")
+        self._tables = dict(mu=mu, W=W, factor_of_state=inv.astype(np.int32), first_factor=n_u)
+        return self._tables
+
+    # ---- the seam methods ----
+    def _check_grid(self, x_trains):
+        if x_trains is None:
+            return
+        x = x_trains.detach().cpu().numpy() if isinstance(x_trains, torch.Tensor) else np.asarray(x_trains)
+        x = x.reshape(-1, self.T) if x.size % self.T == 0 else None
+        if x is None or not np.all(x == self.x_basis[None, :]):
+            raise HgpError("x_train != x_basis (inducing-point branch, GPI.py:470-501) is not built yet; "
+                           "no CPU fallback")
+
+    def _beats(self, y_trains):
+        y = y_trains
+        if not isinstance(y, torch.Tensor):
+            y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64))
+        y = y.to(device=self.device, dtype=F64)
+        if y.dim() == 3:
+            y = y[:, :, 0]
+        return y.contiguous()
+
+    def compute_sq_err_all(self, x_trains, y_trains, no_first=False):
+        """GPI_model.compute_sq_err_all (GPI_model.py:488-547): score of every beat under the
+        time-indexed state of this cluster.  Returns (N,) float64 CUDA tensor."""
+        Y = self._beats(y_trains)
+        N = Y.shape[0]
+        if self.N == 0:
+            return torch.zeros(N, dtype=F64, device=self.device)
+        self._check_grid(x_trains)
+        tb = self.tables()
+        i_vals, first = state_index_map(self.indexes, N, no_first)
+        # `first` beats use a duplicate of state 1 whose factor carries the extra jitter
+        fos = np.concatenate([tb["factor_of_state"], [tb["first_factor"]]]).astype(np.int32)
+        mu = torch.cat([tb["mu"], tb["mu"][1:2] if tb["mu"].shape[0] > 1 else tb["mu"][0:1]], dim=0)
+        s_of = np.where(first, len(fos) - 1, i_vals).astype(np.int32).reshape(N, 1)
+        dev = self.device
+        q = ops.score_pairs(Y, mu, tb["W"], torch.from_numpy(s_of).to(dev), torch.from_numpy(fos).to(dev))
+        return q[:, 0]
+
+    def log_sq_error(self, x_train, y, mean=None, cov=None, C=None, Sigma=None, i=None, proj=False, first=False):
+        """GPI_model.log_sq_error (GPI_model.py:250-286) for params=None; i=None / -1 = last state."""
+        if mean is not None or proj:
+            raise HgpError("log_sq_error with explicit (mean, cov, C, Sigma) / proj is not built yet")
+        self._check_grid(x_train)
+        Y = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
+                                                   dtype=np.float64).reshape(1, -1)))
+        tb = self.tables()
+        nF = self.f_star.shape[0]
+        if i is None:
+            i = -1
+        t = i if i >= 0 else nF + i
+        t = min(t, nF - 1) if self.N > 0 else 0
+        fos = np.concatenate([tb["factor_of_state"], [tb["first_factor"]]]).astype(np.int32)
+        mu = tb["mu"]
+        if first:
+            # jitter is defined on Sigma[0]; the factor table carries it for state 1 only
+            if t != min(1, nF - 1):
+                raise HgpError("first=True is only defined for the first member state")
+            mu = torch.cat([mu, mu[t:t + 1]], dim=0)
+            s = len(fos) - 1
+        else:
+            s = t
+        dev = self.device
+        q = ops.score_pairs(Y, mu, tb["W"], torch.tensor([[s]], dtype=torch.int32, device=dev),
+                            torch.from_numpy(fos).to(dev))
+        return q[0, 0]

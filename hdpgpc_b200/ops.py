@@ -1,0 +1,174 @@
+"""Thin Python wrappers over the C ABI (include/hdpgpc_b200.h).  Tensors are torch CUDA tensors
+(device memory + streams are torch's; the arithmetic is the library's).  No CPU fallback."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+F64 = torch.float64
+I32 = torch.int32
+
+
+def _lib_ready():
+    _lib.require_cuda()
+    return _lib.load()
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise _lib.HgpError("expected a CUDA tensor")
+    return t
+
+
+def launch_count():
+    return int(_lib.load().hgp_launch_count())
+
+
+def pack_leads(Y_ntl):
+    """[N, T, L] -> [L, N, T] (reference layout -> per-lead planes)."""
+    lib = _lib_ready()
+    Y = _dev(Y_ntl).contiguous()
+    N, T, L = Y.shape
+    if L == 1:
+        return Y.reshape(1, N, T)
+    out = torch.empty((L, N, T), dtype=F64, device=Y.device)
+    check(lib.hgp_pack_leads(ptr(Y), N, T, L, ptr(out), stream_ptr()), "hgp_pack_leads")
+    return out
+
+
+def chol_batched(Sigma, add_diag=None, jitter_scale=1e-8, want_logdet=False):
+    """GPI_model._chol_spd for a stack [F, T, T].  Returns (L, info[, logdet])."""
+    lib = _lib_ready()
+    S = _dev(Sigma).contiguous()
+    F, T, _ = S.shape
+    L = torch.empty_like(S)
+    info = torch.empty(F, dtype=I32, device=S.device)
+    logdet = torch.empty(F, dtype=F64, device=S.device) if want_logdet else None
+    if add_diag is not None:
+        add_diag = _dev(add_diag).to(F64).contiguous()
+    check(lib.hgp_chol_batched(ptr(S), F, T, ptr(add_diag), float(jitter_scale), ptr(L), ptr(logdet), ptr(info),
+                               stream_ptr()), "hgp_chol_batched")
+    return (L, info, logdet) if want_logdet else (L, info)
+
+
+def tri_inverse_batched(Lfac):
+    lib = _lib_ready()
+    Lf = _dev(Lfac).contiguous()
+    F, T, _ = Lf.shape
+    W = torch.empty_like(Lf)
+    check(lib.hgp_tri_inverse_batched(ptr(Lf), F, T, ptr(W), stream_ptr()), "hgp_tri_inverse_batched")
+    return W
+
+
+def pack_factors(W):
+    lib = _lib_ready()
+    W = _dev(W).contiguous()
+    F, T, _ = W.shape
+    nd = lib.hgp_packed_factor_bytes(T) // 8
+    out = torch.empty((F, nd), dtype=F64, device=W.device)
+    check(lib.hgp_pack_factors(ptr(W), F, T, ptr(out), stream_ptr()), "hgp_pack_factors")
+    return out
+
+
+def emission_means(C, f, c_idx, f_idx):
+    lib = _lib_ready()
+    C = _dev(C).contiguous()
+    f = _dev(f).contiguous()
+    S = c_idx.numel()
+    T = f.shape[1]
+    mu = torch.empty((S, T), dtype=F64, device=f.device)
+    check(lib.hgp_emission_means(ptr(C), ptr(f), ptr(c_idx), ptr(f_idx), S, T, ptr(mu), stream_ptr()),
+          "hgp_emission_means")
+    return mu
+
+
+def score_tiles(Y, mu, Wpacked, state_of, factor_of_cluster, out=None):
+    lib = _lib_ready()
+    N, T = Y.shape
+    M = state_of.shape[1]
+    q = out if out is not None else torch.empty((N, M), dtype=F64, device=Y.device)
+    check(lib.hgp_score_tiles(ptr(Y), N, T, ptr(mu), ptr(Wpacked), ptr(state_of), ptr(factor_of_cluster), M, ptr(q),
+                              stream_ptr()), "hgp_score_tiles")
+    return q
+
+
+def score_pairs(Y, mu, W, state_of, factor_of_state, pair_n=None, pair_m=None, out=None):
+    lib = _lib_ready()
+    N, T = Y.shape
+    M = state_of.shape[1]
+    q = out if out is not None else torch.zeros((N, M), dtype=F64, device=Y.device)
+    n_pairs = N * M if pair_n is None else pair_n.numel()
+    check(lib.hgp_score_pairs(ptr(Y), N, T, ptr(mu), ptr(W), ptr(state_of), ptr(factor_of_state), M, ptr(pair_n),
+                              ptr(pair_m), n_pairs, ptr(q), stream_ptr()), "hgp_score_pairs")
+    return q
+
+
+def snr_states(Y, mu_sm, snr_state_of, out=None):
+    lib = _lib_ready()
+    N, T = Y.shape
+    M = snr_state_of.shape[1]
+    snr = out if out is not None else torch.empty((N, M), dtype=F64, device=Y.device)
+    check(lib.hgp_snr_states(ptr(Y), N, T, ptr(mu_sm), ptr(snr_state_of), M, ptr(snr), stream_ptr()), "hgp_snr_states")
+    return snr
+
+
+def lead_weights(q_lnm, snr_lnm=None, lead_w=None):
+    """q, snr: [L, N, M].  Returns (qbar [N,M], e [N,M], w [N,L], any_inf flag tensor)."""
+    lib = _lib_ready()
+    L, N, M = q_lnm.shape
+    dev = q_lnm.device
+    qbar = torch.empty((N, M), dtype=F64, device=dev)
+    e = torch.empty((N, M), dtype=F64, device=dev)
+    w = torch.empty((N, L), dtype=F64, device=dev)
+    flags = torch.zeros(1, dtype=I32, device=dev)
+    check(lib.hgp_lead_weights(ptr(q_lnm), ptr(snr_lnm), ptr(lead_w), N, M, L, ptr(qbar), ptr(e), ptr(w), ptr(flags),
+                               stream_ptr()), "hgp_lead_weights")
+    return qbar, e, w, flags
+
+
+class HmmResult:
+    __slots__ = ("alpha", "beta", "marg", "z", "zpair", "boundary_out", "rounds")
+
+
+def hmm_smooth(e, pi, PiT, Pi, Pc, boundary_in=None, has_prev=False, has_next=False, workspace=None):
+    lib = _lib_ready()
+    N, K = e.shape
+    dev = e.device
+    r = HmmResult()
+    r.alpha = torch.empty((N, K), dtype=F64, device=dev)
+    r.beta = torch.empty((N, K), dtype=F64, device=dev)
+    r.marg = torch.empty(N, dtype=F64, device=dev)
+    r.z = torch.empty(N, dtype=I32, device=dev)
+    r.zpair = torch.empty(N, dtype=I32, device=dev)
+    r.boundary_out = torch.empty(2 * K, dtype=F64, device=dev)
+    need = lib.hgp_hmm_workspace_bytes(N, K)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    rounds = ctypes.c_int(0)
+    check(lib.hgp_hmm_smooth(ptr(e), N, K, ptr(pi), ptr(PiT), ptr(Pi), ptr(Pc), ptr(boundary_in), int(has_prev),
+                             int(has_next), ptr(r.alpha), ptr(r.beta), ptr(r.marg), ptr(r.z), ptr(r.zpair),
+                             ptr(r.boundary_out), ptr(workspace), workspace.numel(), ctypes.byref(rounds),
+                             stream_ptr()), "hgp_hmm_smooth")
+    r.rounds = rounds.value
+    return r
+
+
+def suffstats(z, zpair, qbar, is_first_slice=True, workspace=None):
+    """Returns (Nm [K], trans [K,K], start [K], Qem [1]) -- one packed f64 tensor is also returned
+    so the multi-GPU path can all-reduce it in one call."""
+    lib = _lib_ready()
+    N, K = qbar.shape
+    dev = qbar.device
+    packed = torch.empty(K + K * K + K + 1, dtype=F64, device=dev)
+    Nm = packed[:K]
+    trans = packed[K:K + K * K].view(K, K)
+    start = packed[K + K * K:K + K * K + K]
+    Qem = packed[-1:]
+    need = lib.hgp_suffstats_workspace_bytes(N, K)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib.hgp_suffstats(ptr(z), ptr(zpair), ptr(qbar), N, K, int(is_first_slice), ptr(Nm), ptr(trans), ptr(start),
+                            ptr(Qem), ptr(workspace), workspace.numel(), stream_ptr()), "hgp_suffstats")
+    return Nm, trans, start, Qem, packed

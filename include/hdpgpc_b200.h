@@ -1,0 +1,133 @@
+/*
+ * hdpgpc_b200 -- C ABI of the B200-native HDP-GPC variational E-step hot path.
+ *
+ * The reference (AdrianPerezHerrero/HDP-GPC) is pure Python/torch and has no FFI; the drop-in
+ * boundary is the Python method surface listed in SURVEY.md section 8b.  Each entry point
+ * below names the reference method(s) whose arithmetic it replaces (paths are relative to
+ * /root/reference/hdpgpc/hdpgpc/).  INTEGRATION.md shows the ctypes binding and the patch a
+ * maintainer of the reference would apply.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host
+ *   - matrices are row-major float64, contiguous; indices are int32; sizes are int64/int
+ *   - every call takes the CUDA stream (as void*, a cudaStream_t) it must run on and is asynchronous
+ *     (exception: hgp_hmm_smooth synchronises the stream once per repair round to read a flag)
+ *   - no allocation inside: scratch is passed in, sized by the matching *_workspace_bytes call
+ *   - return value: 0 = launched OK, < 0 = -(cudaError_t), > 0 = argument error code (HGP_E_*)
+ *   - numerical failure (non-SPD matrix) is reported per matrix in an `info` array like LAPACK:
+ *     0 = ok, j+1 = leading minor of order j+1 not positive; the Python layer turns it into the
+ *     reference's torch.linalg.LinAlgError behaviour (GPI_model.py:1068-1071)
+ */
+#ifndef HDPGPC_B200_H
+#define HDPGPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGP_E_BADARG 1
+#define HGP_E_UNSUPPORTED 2
+#define HGP_E_WORKSPACE 3
+
+/* Library / build information. */
+int hgp_version(void);                 /* 100*major + minor */
+const char* hgp_build_info(void);      /* arch, nvcc version, build flags */
+const char* hgp_last_error(void);      /* text of the last failure on this thread */
+/* Number of kernels this library has launched since load (all streams); bench.py reads it. */
+int64_t hgp_launch_count(void);
+
+/* ---- beat layout ---------------------------------------------------------------------
+ * Reference beats are Y[N, T, L] (tests/test_offline.py:31; sliced per lead as
+ * y_trains[:, :, [ld]] at GPI_HDP.py:2901, :2985).  Kernels want one contiguous [N, T] plane
+ * per lead: Yp[L, N, T]. */
+int hgp_pack_leads(const double* Y_ntl, int64_t N, int T, int L, double* Y_lnt, void* stream);
+
+/* ---- SPD factorisation: GPI_model._chol_spd (GPI_model.py:83-87) -------------------------
+ * For f in [0, F):  M = Sigma[f] + add_diag[f] * I   (add_diag may be NULL; the `first` rule
+ *                                                     GPI_model.py:271-273, :527-529)
+ *                   Lfac[f] = chol( 0.5 (M + M^T) + jitter_scale * max(mean|diag M|, eps) * I )
+ * Lfac is lower triangular with zeros above the diagonal.  logdet (may be NULL) receives
+ * 2 * sum(log diag L) -- an extra output, never part of the emission score. */
+int hgp_chol_batched(const double* Sigma, int64_t F, int T, const double* add_diag, double jitter_scale,
+                     double* Lfac, double* logdet, int* info, void* stream);
+
+/* W[f] = Lfac[f]^{-1} (lower triangular, zeros above the diagonal).  With it the Mahalanobis
+ * term d^T Sigma^{-1} d of GPI_model.py:109-113 / :280-285 is |W d|^2 (one triangular product;
+ * the reference's cholesky_solve does two). */
+int hgp_tri_inverse_batched(const double* Lfac, int64_t F, int T, double* W, void* stream);
+
+/* Re-order W[F, T, T] into the DMMA-fragment-ordered, k-chunked stream the tile kernel reads
+ * with 1-D bulk (TMA) copies.  Bytes per factor: hgp_packed_factor_bytes(T). */
+int64_t hgp_packed_factor_bytes(int T);
+int hgp_pack_factors(const double* W, int64_t F, int T, double* Wpacked, void* stream);
+
+/* ---- emission scores: GPI_model.compute_sq_err_all (GPI_model.py:488-547),
+ *      GPI_model.log_sq_error (:250-286), _gaussian_score_shared_cov (:92-113) ------------------
+ * One lead plane.  For every beat n and cluster m:
+ *     s = state_of[n*M + m]            (row of `mu`, the emission mean C_i f_i of GPI_model.observe
+ *                                       :626-662; -1 => q = 0, "cluster has no members" :494-495)
+ *     q[n*M + m] = -0.5 * | W_f (Y[n] - mu[s]) |^2 - 0.5 * T * log(2 pi)        (no log-det)
+ *
+ * hgp_score_tiles: f = factor_of_cluster[m]; all beats, W in packed form; tensor-core (DMMA) path.
+ * hgp_score_pairs: explicit list of (n, m) pairs with f = factor_of_state[s]; W in plain form;
+ *                  used for the states whose covariance differs from the cluster's shared one
+ *                  (per-state Sigma_i when estimation_limit=None, the `first` jitter) and as the
+ *                  general path when every state has its own factor. */
+int hgp_score_tiles(const double* Y, int64_t N, int T, const double* mu, const double* Wpacked,
+                    const int* state_of, const int* factor_of_cluster, int M, double* q, void* stream);
+int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const double* W,
+                    const int* state_of, const int* factor_of_state, int M,
+                    const int* pair_n, const int* pair_m, int64_t n_pairs, double* q, void* stream);
+
+/* ---- lead weighting: GPI_HDP.compute_snr (GPI_HDP.py:732-748), weight_mean (:685-701),
+ *      LogLik (:632-661) ------------------------------------------------------------------
+ * snr[n*M + m] = 10 log10( (sum mu^2 + eps) / (sum (mu - y)^2 + eps) ),  mu = mu_sm[snr_state_of[n*M+m]]
+ * (the smoothed latent mean f_star_sm[j], j = clip(find_closest_lower(n), 1, len-1)). */
+int hgp_snr_states(const double* Y, int64_t N, int T, const double* mu_sm, const int* snr_state_of,
+                   int M, double* snr, void* stream);
+/* q, snr: [L, N, M] planes.  w[n, ld] = softmax_ld( max_m snr[ld, n, m] ) (or lead_w[N, L] when snr is
+ * NULL: the saved self.snr_norm), qbar[n, m] = sum_ld q[ld, n, m] w[n, ld];
+ * e[n, k] = nan_to_num(exp(qn - rowmax(qn)), 1e-8) with qn = qbar - rowmax(qbar), the subtraction
+ * skipped for ALL rows when any row max is +-inf (LogLik's early return, :646-648).
+ * flags[0] receives that "any inf" bit.  wout (may be NULL) receives w[N, L]. */
+int hgp_lead_weights(const double* q, const double* snr, const double* lead_w, int64_t N, int M, int L,
+                     double* qbar, double* e, double* wout, int* flags, void* stream);
+
+/* ---- HMM smoothing and hard responsibilities: GPI_HDP.forward (GPI_HDP.py:3546-3610),
+ *      backward (:3612-3649), coupled_state_coef (:3651-3699), _safe_exp (:338-350) -------------
+ * Operands pi[K], PiT[K,K], Pi[K,K], Pc[K,K] are built on the host exactly as the reference does
+ * (digamma, max-shift, floors); the device scans.  The scan is chunk-parallel and EXACT: chunks
+ * start from a guess, then are repaired from their predecessor's true boundary message until
+ * every message is bit-identical to the sequential recursion.
+ * alpha, beta: [N, K] outputs (normalised messages); marg[N] (may be NULL) = margPrObs of forward().
+ * z[N] = argmax_k log(alpha beta),
+ * zpair[N] = argmax over the flattened KxK pair coefficient (row 0 -> 0).
+ * boundary_in (may be NULL): alpha_in[K] then beta_in[K] -- messages entering this slice from the
+ * neighbouring ranks when the beat sequence is sharded (has_prev / has_next say which are valid).
+ * boundary_out[2K]: alpha of the slice's last beat, then (beta (.) e) of the slice's first beat
+ * -- what the neighbours need.  Returns the number of repair rounds used in rounds_host. */
+int64_t hgp_hmm_workspace_bytes(int64_t N, int K);
+int hgp_hmm_smooth(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
+                   const double* Pc, const double* boundary_in, int has_prev, int has_next,
+                   double* alpha, double* beta, double* marg, int* z, int* zpair, double* boundary_out,
+                   void* workspace, int64_t workspace_bytes, int* rounds_host, void* stream);
+
+/* ---- sufficient statistics: include_batch (GPI_HDP.py:890-892), compute_q_elbo (:1805) --------
+ * Nm[K] = sum_n [z_n = k];  trans[K,K] = sum_n onehot(zpair_n) (counts, exact integers in f64);
+ * start[K] = onehot(z_0) if is_first_slice else 0;  Qem[0] = sum_n qbar[n, z_n] (fixed-order sum). */
+int64_t hgp_suffstats_workspace_bytes(int64_t N, int K);
+int hgp_suffstats(const int* z, const int* zpair, const double* qbar, int64_t N, int K, int is_first_slice,
+                  double* Nm, double* trans, double* start, double* Qem,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- emission means: GPI_model.observe (GPI_model.py:626-662) on the basis grid ---------------
+ * mu[s] = C[c_idx[s]] @ f[f_idx[s]]  for s in [0, S)   (C: [nC, T, T], f: [nF, T]). */
+int hgp_emission_means(const double* C, const double* f, const int* c_idx, const int* f_idx, int64_t S, int T,
+                       double* mu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDPGPC_B200_H */

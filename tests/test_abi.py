@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports exactly what
+include/hdpgpc_b200.h declares; the product refuses to run without a GPU; the product never imports
+the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "hdpgpc_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hgp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import hdpgpc_b200
+    from hdpgpc_b200 import _lib
+    path = hdpgpc_b200.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/hdpgpc_b200.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == syms, "ctypes prototypes out of sync with the header"
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\bT (hgp_[a-z0-9_]+)", out)))
+    assert exported == syms, "library exports symbols the header does not declare (or vice versa)"
+
+
+def test_library_is_sm100a_with_tensor_and_tma_sass():
+    import hdpgpc_b200
+    path = hdpgpc_b200.build()
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "DMMA" in sass            # FP64 tensor-core instruction of the tile kernel
+    assert "UBLKCP" in sass          # bulk async copy (TMA) of the factor stream
+    assert "USETMAXREG" in sass      # warpgroup register re-balancing
+
+
+def test_no_cpu_fallback():
+    import torch
+    import hdpgpc_b200
+    from hdpgpc_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hdpgpc_b200.HgpError):
+        ops.chol_batched(torch.eye(4, dtype=torch.float64).reshape(1, 4, 4))
+    with pytest.raises(hdpgpc_b200.HgpError):
+        ops.pack_leads(torch.zeros(2, 4, 2, dtype=torch.float64))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hdpgpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+                assert "/root/reference" not in txt, f
+    code = "import sys; import hdpgpc_b200, hdpgpc_b200.synthetic; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_host_operands_match_oracle(golden):
+    """The K-sized HMM operands and the state index maps are host logic of the product; they must
+    agree with the oracle's restatement bit for bit."""
+    import numpy as np
+    from hdpgpc_b200 import hdp, model
+    from oracle import hdpgpc_oracle as O
+    z = golden("hmm_synth")
+    for c in range(int(z["n_cases"])):
+        tt, st = z[f"c{c}_transTheta"], z[f"c{c}_startTheta"]
+        K = z[f"c{c}_q"].shape[1]
+        sp, tp = hdp.expected_log_pi(tt, st, K)
+        assert np.allclose(sp, z[f"c{c}_startPi"], rtol=1e-13, atol=0)
+        assert np.allclose(tp, z[f"c{c}_transPi"], rtol=1e-13, atol=0)
+        assert np.allclose(hdp.compute_trans_A(tt, K), z[f"c{c}_trans_A"], rtol=1e-13, atol=0)
+        osp, otp = O.start_trans_pi(tt, st, K)
+        assert np.array_equal(sp, osp) and np.array_equal(tp, otp)
+        mine = hdp.hmm_operands(tt, sp, K)
+        ref = O.hmm_operands(tt, sp, K)
+        for a, b in zip(mine, ref):
+            assert np.array_equal(a, b)
+    idx = [3, 4, 9, 17]
+    gp = type("G", (), {"indexes": idx})()
+    i1, f1 = model.state_index_map(idx, 25)
+    og = O.OracleGP.__new__(O.OracleGP)
+    og.indexes = idx
+    i2, f2 = og.state_index_map(25)
+    assert np.array_equal(i1, i2) and np.array_equal(f1, f2)
+    assert np.array_equal(model.snr_state_index(idx, 5, 25), O.snr_state_index(idx, 5, 25))

@@ -1,0 +1,144 @@
+"""Pins the CPU oracle (oracle/hdpgpc_oracle.py) to the reference: every fixture under tests/golden/
+was produced by the unmodified reference (tests/golden/generate_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import hdpgpc_oracle as O
+
+OFFLINE_FULL = ["offline_rec100_T30_L1", "offline_rec102_T30_L2"]
+OFFLINE_ALL = OFFLINE_FULL + ["offline_rec100_T90_L1"]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def test_hmm_synthetic_cases(golden):
+    z = golden("hmm_synth")
+    for c in range(int(z["n_cases"])):
+        g = lambda k: z[f"c{c}_{k}"]
+        r = O.estep_responsibilities(g("q"), g("snr"), g("transTheta"), g("startTheta"))
+        assert rel(r["qbar"], g("qbar")) < 1e-13
+        assert np.max(np.abs(r["alpha"] - g("alpha"))) < 1e-12
+        assert rel(r["beta"], g("beta")) < 1e-11
+        assert rel(r["marg"], g("margprob")) < 1e-11
+        assert np.array_equal(r["z"], g("z"))
+        assert np.array_equal(r["zpair"], g("zpair"))
+        assert np.array_equal(r["transStateCount"], g("transStateCount"))
+        assert np.array_equal(r["startStateCount"], g("startStateCount"))
+        assert np.array_equal(r["Nm"], g("Nm"))
+        assert abs(r["Q_em"] - float(g("Q_em"))) <= 1e-12 * abs(float(g("Q_em")))
+        assert str(g("respPair_dtype")) == "torch.float32"   # reference quirk kept in the mirror
+
+
+@pytest.mark.parametrize("name", OFFLINE_FULL)
+def test_seam_functions_from_dumped_state(golden, name):
+    z = golden(name)
+    M, L = int(z["M"]), int(z["L"])
+    Y, Ynew = z["data"], z["new"]
+    N = Y.shape[0]
+    gps = [[O.OracleGP.from_dump(z, f"gp_{ld}_{m}_") for m in range(M)] for ld in range(L)]
+    q = np.zeros((N, M, L)); qnf = np.zeros_like(q); ql = np.zeros_like(q); snr = np.zeros_like(q)
+    qn = np.zeros((Ynew.shape[0], M, L)); sn = np.zeros_like(qn)
+    for ld in range(L):
+        for m in range(M):
+            gp = gps[ld][m]
+            q[:, m, ld] = gp.compute_sq_err_all(None, Y[:, :, ld])
+            qnf[:, m, ld] = gp.compute_sq_err_all(None, Y[:, :, ld], no_first=True)
+            ql[:, m, ld] = gp.compute_q_lat_all(N)
+            snr[:, m, ld] = O.compute_snr(Y[:, :, ld], gp)
+            qn[:, m, ld] = [gp.log_sq_error(None, y, i=-1) for y in Ynew[:, :, ld]]
+            sn[:, m, ld] = O.compute_snr(Ynew[:, :, ld], gp)
+    assert rel(q, z["q_all"]) < 1e-12
+    assert rel(qnf, z["q_all_nofirst"]) < 1e-12
+    assert rel(ql, z["q_lat_all"]) < 1e-12
+    assert rel(snr, z["snr_all"]) < 1e-12
+    assert rel(qn, z["q_new"]) < 1e-12
+    assert rel(sn, z["snr_new"]) < 1e-12
+    for pre, qq, ss in (("train_", z["q_all"], z["snr_all"]), ("new_", z["q_new"], z["snr_new"])):
+        r = O.estep_responsibilities(qq, ss, z["transTheta"], z["startTheta"])
+        assert np.array_equal(r["z"], z[pre + "z"])
+        assert np.array_equal(r["zpair"], z[pre + "zpair"])
+        assert np.max(np.abs(r["alpha"] - z[pre + "alpha"])) < 1e-12
+        assert rel(r["beta"], z[pre + "beta"]) < 1e-10
+        assert np.array_equal(r["transStateCount"], z[pre + "transStateCount"])
+        assert np.array_equal(r["Nm"], z[pre + "Nm"])
+        assert rel(r["Q_em"], z[pre + "Q_em"]) < 1e-13
+    r = O.estep_responsibilities(z["q_all"], None, z["transTheta"], z["startTheta"], snr_norm=z["snr_norm"])
+    assert np.array_equal(r["z"], z["saved_z"])
+    assert np.array_equal(r["z"] if False else O.estep_responsibilities(
+        z["q_new"], z["snr_new"], z["transTheta"], z["startTheta"])["z"], z["new_cluster_new_batch"])
+    lik = np.array([[gps[ld][m].return_LDS_param_likelihood() for m in range(M)] for ld in range(L)])
+    assert rel(lik, z["lds_param_lik"]) < 1e-12
+    Nm = z["train_Nm"]
+    fl = [O.full_LDS_elbo(gps[ld], Nm, 5) for ld in range(L)]
+    assert rel(fl, z["elbo_full_LDS"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", OFFLINE_ALL)
+def test_chain_replay(golden, name):
+    """Fresh model -> Kalman / pair smoother / MNIW per member -> full RTS pass -> scores
+    (GPI_model.full_pass_weighted).  The first Kalman step solves against K + noise*I with
+    cond ~1e7, so different LAPACK builds already differ at ~1e-10; the bar is the north-star 1e-8."""
+    z = golden(name)
+    Y = z["data"]
+    full = f"chain_0_Sigma" in z.files
+    for m in range(int(z["n_chain"])):
+        pre = f"chain_{m}_"
+        gp = O.OracleGP(z["x_basis"], z["kernel_def"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]),
+                        free_deg=int(z["free_deg_MNIV"]))
+        q, ql = gp.full_pass_weighted(Y[:, :, 0], z[pre + "resp"], fitted_kernel=z[pre + "kernel"])
+        assert gp.indexes == [int(i) for i in z[pre + "indexes"]]
+        assert rel(q, z[pre + "q"]) < 1e-8
+        assert rel(ql, z[pre + "q_lat"]) < 1e-8
+        assert rel(O.compute_snr(Y[:, :, 0], gp), z[pre + "snr"]) < 1e-8
+        scale = np.max(np.abs(z[pre + "f_star"]))
+        assert np.max(np.abs(np.stack(gp.f_star) - z[pre + "f_star"][:, :, 0])) < 1e-8 * scale
+        assert np.max(np.abs(np.stack(gp.f_star_sm) - z[pre + "f_star_sm"][:, :, 0])) < 1e-8 * scale
+        for nm in ["cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma"]:
+            mine = getattr(gp, nm)
+            if full:
+                ref = z[pre + nm]
+                assert len(mine) == ref.shape[0]
+                assert np.max(np.abs(np.stack(mine) - ref)) < 1e-8 * np.max(np.abs(ref))
+            else:
+                assert len(mine) == int(z[pre + nm + "_len"])
+                ref = z[pre + nm + "_last"]
+                assert np.max(np.abs(mine[-1] - ref)) < 1e-8 * np.max(np.abs(ref))
+                chk = np.array([[np.trace(v), np.linalg.norm(v)] for v in mine])
+                assert rel(chk, z[pre + nm + "_chk"][:, :2]) < 1e-8
+
+
+def test_inducing_grid(golden):
+    """x_train != x_basis: pred_dist kernel branch (GPI.py:470-501)."""
+    z = golden("inducing_T30")
+    gp = O.OracleGP.from_dump(z, "gp_")
+    Y = z["data"][:, :, 0]
+    x_off, x_sub = z["x_off"].reshape(-1), z["x_sub"].reshape(-1)
+    for k, i in enumerate([1, 4, 9]):
+        f, c = gp.observe(x_off, i)
+        assert np.max(np.abs(f - z[f"obs_off_{i}_mean"][:, 0])) < 1e-9 * np.max(np.abs(f))
+        assert np.max(np.abs(c - z[f"obs_off_{i}_cov"])) < 1e-12 * np.max(np.abs(c))
+        s = [gp.log_sq_error(x_off, Y[n], i=i) for n in range(6)]
+        assert rel(s, z["score_off"][k]) < 1e-11
+    assert rel([gp.log_sq_error(x_off, Y[n], i=-1) for n in range(6)], z["score_off_last"]) < 1e-11
+    assert rel([gp.log_sq_error(x_sub, Y[n, ::2], i=3) for n in range(6)], z["score_sub"]) < 1e-11
+
+
+def test_table_form_matches_object_form(golden):
+    """score_states / snr_states (the struct-of-arrays form the device consumes) == per-object methods."""
+    z = golden("offline_rec100_T30_L1")
+    M = int(z["M"])
+    Y = z["data"][:, :, 0]
+    N = Y.shape[0]
+    for m in range(M):
+        gp = O.OracleGP.from_dump(z, f"gp_0_{m}_")
+        i_vals, first = gp.state_index_map(N)
+        nF = len(gp.f_star)
+        mu = np.stack([gp.observe_state(t)[0] for t in range(nF)] + [gp.observe_state(1)[0]])
+        Sig = np.stack([gp.observe_state(t)[1] for t in range(nF)] + [gp.observe_state(1)[1]])
+        add = np.zeros(nF + 1); add[-1] = gp.first_jitter()
+        s_of = np.where(first, nF, i_vals).reshape(N, 1)
+        q = O.score_states(Y, mu, Sig, s_of, np.arange(nF + 1), add)[:, 0]
+        assert rel(q, z["q_all"][:, m, 0]) < 1e-12
