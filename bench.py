@@ -195,14 +195,13 @@ def run_ours(args):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ops.score_tiles(tb.Y, tb.mu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[ld])
+            ops.score_tiles(tb.Y, tb.mu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[ld])
+            if record:
                 e1.record()
                 tile_events.append((e0, e1))
-            else:
-                ops.score_tiles(tb.Y, tb.mu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[ld])
+            tb.snr(eng.snr[ld])
             if tb.pair_n is not None:
                 ops.score_pairs(tb.Y, tb.mu, tb.W, tb.state_of, tb.factor_of_state, tb.pair_n, tb.pair_m, out=eng.q[ld])
-            tb.snr(eng.snr[ld])
         qbar, e, w, hm = eng.responsibilities()
         return eng.statistics(qbar, hm), hm
 

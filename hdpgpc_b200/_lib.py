@@ -21,7 +21,7 @@ PROTOTYPES = {
     "hgp_tri_inverse_batched": (_int, [_p, _i64, _int, _p, _p]),
     "hgp_packed_factor_bytes": (_i64, [_int]),
     "hgp_pack_factors": (_int, [_p, _i64, _int, _p, _p]),
-    "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p]),
+    "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p]),
     "hgp_score_pairs": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _i64, _p, _p]),
     "hgp_snr_states": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p]),
     "hgp_lead_weights": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p]),
@@ -46,10 +46,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIBPATH):
-        raise HgpError(f"{LIBPATH} is missing: run `python -m hdpgpc_b200.build` (needs nvcc). "
+    path = os.environ.get("HGP_LIB", LIBPATH)     # HGP_LIB: A/B-test another build of the same ABI
+    if not os.path.exists(path):
+        raise HgpError(f"{path} is missing: run `python -m hdpgpc_b200.build` (needs nvcc). "
                        "hdpgpc_b200 has no CPU fallback.")
-    lib = ctypes.CDLL(LIBPATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -9,10 +9,12 @@
 //     fragment-ordered k-chunks with 1-D bulk async copies (TMA, completion on an mbarrier) through a
 //     4-stage shared-memory ring, and builds the matching 8 x 64 slice of D = Y - mu (beat tile
 //     resident in shared memory, means gathered through L2) directly in B-fragment order;
-//   * 2 consumer warpgroups (8 warps, setmaxnreg.inc): row blocks of 8 are dealt round-robin to warps so that the triangular
+//   * 2 consumer warpgroups (8 warps, setmaxnreg.inc): row blocks of 8 are dealt to warps in a mirrored
+//     order so that the triangular
 //     shrinkage (row block rb only needs k-chunks kc <= rb) stays balanced over the 4 SM
 //     sub-partitions; each warp keeps its 32 x 64 slice of z in registers (64 f64 accumulators/lane).
 #include "hgp_common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -61,9 +63,16 @@ constexpr int W_STAGE_BYTES = MAX_NRB * 512;   // 16 KB
 constexpr int D_STAGE_BYTES = 8 * BT * 8;      // 4 KB
 // Register re-balancing between the warpgroups (setmaxnreg): the kernel launches with 168
 // registers/thread (3 warps per SM sub-partition); consumers grow, producers shrink.
-// Per sub-partition: 2 consumer warps x 32 x 224 + 1 producer warp x 32 x 56 = 16128 <= 16384.
-#define HGP_CONSUMER_REGS 224
-#define HGP_PRODUCER_REGS 56
+// Per sub-partition: 2 consumer warps x 32 x 216 + 1 producer warp x 32 x 72 = 16128 <= 16384.
+#ifndef HGP_PF
+#define HGP_PF 2
+#endif
+constexpr int PF = HGP_PF;     // producer prefetch depth (k-chunks of gathered means in flight)
+#define HGP_CONSUMER_REGS 216
+#define HGP_PRODUCER_REGS 72
+
+__device__ __forceinline__ int chunk_of(int i, int nrb) { (void)nrb; return i; }   // k-chunks in ascending order
+
 
 struct TileSmem {
     // offsets (bytes) into dynamic shared memory
@@ -81,11 +90,64 @@ __host__ __device__ inline TileSmem tile_smem_layout(int Tp) {
     return s;
 }
 
+// Beat tile -> shared memory, zero padded (rows n >= N, samples t >= T), by all warps of the CTA.
+__device__ __forceinline__ void load_beat_tile(double* Ytile, const double* __restrict__ Y, int64_t N, int T, int YP,
+                                               int64_t n0, int warp, int lane) {
+    const bool vec = ((T & 1) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+    for (int c = warp; c < BT; c += NCW + NPW) {
+        const int64_t n = n0 + c;
+        double* dst = Ytile + c * YP;
+        if (n < N && vec) {
+            const double2* src = reinterpret_cast<const double2*>(Y + n * T);
+            for (int t2 = lane; t2 < YP / 2; t2 += 32)
+                reinterpret_cast<double2*>(dst)[t2] = (2 * t2 < T) ? src[t2] : make_double2(0.0, 0.0);
+        } else {
+            const double* src = Y + n * T;
+            for (int t = lane; t < YP; t += 32) dst[t] = (n < N && t < T) ? src[t] : 0.0;
+        }
+    }
+}
+
+// One k-chunk for a warp whose row blocks j >= J0 are active (T = 256 fast path): no per-block tests,
+// so the A/B fragment loads of the whole chunk are issued up front and the 16 * (4 - J0) tensor-core
+// instructions follow as one straight-line stream.
+template <int J0>
+__device__ __forceinline__ void fast_chunk(double (&acc)[4][8][2], uint32_t it, int kc, int rb0, int rb1, int rb2,
+                                           int rb3, int lane, const unsigned char* Wst, const unsigned char* Dst,
+                                           uint64_t* full_bar, uint64_t* empty_bar) {
+    const int stage = it & (STAGES - 1);
+    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+    if (J0 < 4) {
+        const double2* ds = reinterpret_cast<const double2*>(Dst + stage * D_STAGE_BYTES) + lane;
+        const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane - kc * 32;
+        double2 b[8];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) b[nt] = ds[nt * 32];
+        double2 a[4];
+        if (J0 <= 0) a[0] = ws[rb0 * 32];
+        if (J0 <= 1) a[1] = ws[rb1 * 32];
+        if (J0 <= 2) a[2] = ws[rb2 * 32];
+        if (J0 <= 3) a[3] = ws[rb3 * 32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= J0) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a[j].x, b[nt].x);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a[j].y, b[nt].y);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+}
+
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu,
                    const double* __restrict__ Wpacked, int64_t packed_doubles, const int* __restrict__ state_of,
                    const int* __restrict__ factor_of_cluster, int M, int m_per_item, int m_splits, int64_t n_items,
-                   double* __restrict__ q) {
+                   double* __restrict__ q, const double* __restrict__ mu_sm, const int* __restrict__ snr_state_of,
+                   double* __restrict__ snr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nrb = (T + 7) / 8;
     const int Tp = nrb * 8;
@@ -99,7 +161,9 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
     uint64_t* empty_bar = full_bar + STAGES;
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the role / row-block branches
+    // need no reconvergence (no WARPSYNC / BSSY around the tensor-core blocks)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -123,55 +187,81 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
             const int m_begin = (int)(item % m_splits) * m_per_item;
             const int m_end = min(M, m_begin + m_per_item);
             const int64_t n0 = tile * BT;
-            // ---- beat tile -> shared (coalesced), zero padded ----
-            for (int c = pw; c < BT; c += NPW) {
-                const int64_t n = n0 + c;
-                const double* yrow = Y + n * T;
-                for (int t = lane; t < YP; t += 32) Ytile[c * YP + t] = (n < N && t < T) ? yrow[t] : 0.0;
-            }
-            asm volatile("bar.sync 2, 128;" ::: "memory");   // producers only: tile complete
+            load_beat_tile(Ytile, Y, N, T, YP, n0, warp, lane);
+            __syncthreads();   // tile complete (all 12 warps load it)
             const double* y0 = Ytile + ((2 * pw) * 8 + nn) * YP + kk;
             const double* y1 = y0 + 8 * YP;
+            // State indices are fetched two clusters ahead and the mean rows of cluster m+1 are pulled into L2
+            // while cluster m is produced: the per-chunk gathers below then hit L2 instead of HBM.
+            const int64_t na = n0 + (2 * pw) * 8 + nn, nb = na + 8;
+            auto load_state = [&](int m, int& sa, int& sb) {
+                sa = (m < m_end && na < N) ? state_of[na * M + m] : -1;
+                sb = (m < m_end && nb < N) ? state_of[nb * M + m] : -1;
+            };
+            auto prefetch_rows = [&](int sa, int sb) {
+                // the 4 lanes of a column (kk = 0..3) split its row into 128-byte lines
+                const int lines = (T * 8 + 127) / 128;
+                for (int l = kk; l < lines; l += 4) {
+                    if (sa >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(mu + (int64_t)sa * T + l * 16));
+                    if (sb >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(mu + (int64_t)sb * T + l * 16));
+                }
+            };
+            int sa, sb, sa1, sb1, sa2, sb2;
+            load_state(m_begin, sa, sb);
+            load_state(m_begin + 1, sa1, sb1);
+            prefetch_rows(sa, sb);
             for (int m = m_begin; m < m_end; ++m) {
                 const unsigned char* Wp =
                     reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
-                const int64_t na = n0 + (2 * pw) * 8 + nn, nb = na + 8;
-                const int sa = (na < N) ? state_of[na * M + m] : -1;
-                const int sb = (nb < N) ? state_of[nb * M + m] : -1;
+                load_state(m + 2, sa2, sb2);
+                prefetch_rows(sa1, sb1);
                 const double* ma = (sa >= 0) ? mu + (int64_t)sa * T + kk : nullptr;
                 const double* mb = (sb >= 0) ? mu + (int64_t)sb * T + kk : nullptr;
-                // means of chunk 0 (prefetched one chunk ahead afterwards)
-                double ca0 = (ma && kk < T) ? __ldg(ma) : 0.0, ca1 = (ma && kk + 4 < T) ? __ldg(ma + 4) : 0.0;
-                double cb0 = (mb && kk < T) ? __ldg(mb) : 0.0, cb1 = (mb && kk + 4 < T) ? __ldg(mb + 4) : 0.0;
-                uint32_t off = 0;   // byte offset of chunk kc in the packed factor
-                for (int kc = 0; kc < nrb; ++kc, ++it) {
-                    const int stage = it % STAGES;
-                    const uint32_t phase = (it / STAGES) & 1;
-                    const uint32_t bytes = (uint32_t)(nrb - kc) * 512u;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (pw == 0 && lane == 0) {
-                        mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                        bulk_g2s(Wst + stage * W_STAGE_BYTES, Wp + off, bytes, &full_bar[stage]);
+                // The means are gathered through L2 (~650 cycles): keep PF chunks of them in flight in a
+                // register ring so the producer never waits on a load it issued less than PF steps ago.
+                double ring[PF][4];
+                auto load_chunk = [&](int i, double (&dst)[4]) {
+                    dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
+                    if (i < nrb) {
+                        const int o = 8 * chunk_of(i, nrb);
+                        const bool w0 = o + kk < T, w1 = o + kk + 4 < T;
+                        if (ma) { if (w0) dst[0] = __ldg(ma + o); if (w1) dst[1] = __ldg(ma + o + 4); }
+                        if (mb) { if (w0) dst[2] = __ldg(mb + o); if (w1) dst[3] = __ldg(mb + o + 4); }
                     }
-                    off += bytes;
-                    double na0 = 0.0, na1 = 0.0, nb0 = 0.0, nb1 = 0.0;
-                    const int tn = (kc + 1) * 8 + kk;
-                    if (kc + 1 < nrb) {
-                        if (ma) { if (tn < T) na0 = __ldg(ma + 8 * (kc + 1)); if (tn + 4 < T) na1 = __ldg(ma + 8 * (kc + 1) + 4); }
-                        if (mb) { if (tn < T) nb0 = __ldg(mb + 8 * (kc + 1)); if (tn + 4 < T) nb1 = __ldg(mb + 8 * (kc + 1) + 4); }
+                };
+#pragma unroll
+                for (int p = 0; p < PF; ++p) load_chunk(p, ring[p]);
+                for (int i0 = 0; i0 < nrb; i0 += PF) {
+#pragma unroll
+                    for (int p = 0; p < PF; ++p) {
+                        const int i = i0 + p;
+                        if (i < nrb) {
+                            const int kc = chunk_of(i, nrb);
+                            const int stage = it % STAGES;
+                            const uint32_t phase = (it / STAGES) & 1;
+                            const uint32_t bytes = (uint32_t)(nrb - kc) * 512u;
+                            const uint32_t off = 512u * (uint32_t)(kc * nrb - (kc * (kc - 1)) / 2);
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (pw == 0 && lane == 0) {
+                                mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                                bulk_g2s(Wst + stage * W_STAGE_BYTES, Wp + off, bytes, &full_bar[stage]);
+                            }
+                            double2* dstage = reinterpret_cast<double2*>(Dst + stage * D_STAGE_BYTES) + (2 * pw) * 32 + lane;
+                            double2 va, vb;   // rows t >= T: y = 0 and mu = 0
+                            va.x = ma ? y0[kc * 8] - ring[p][0] : 0.0;
+                            va.y = ma ? y0[kc * 8 + 4] - ring[p][1] : 0.0;
+                            vb.x = mb ? y1[kc * 8] - ring[p][2] : 0.0;
+                            vb.y = mb ? y1[kc * 8 + 4] - ring[p][3] : 0.0;
+                            dstage[0] = va;
+                            dstage[32] = vb;
+                            load_chunk(i + PF, ring[p]);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&full_bar[stage]);
+                            ++it;
+                        }
                     }
-                    double2* dstage = reinterpret_cast<double2*>(Dst + stage * D_STAGE_BYTES) + (2 * pw) * 32 + lane;
-                    double2 va, vb;   // rows t >= T: y = 0 and mu = 0
-                    va.x = ma ? y0[kc * 8] - ca0 : 0.0;
-                    va.y = ma ? y0[kc * 8 + 4] - ca1 : 0.0;
-                    vb.x = mb ? y1[kc * 8] - cb0 : 0.0;
-                    vb.y = mb ? y1[kc * 8 + 4] - cb1 : 0.0;
-                    dstage[0] = va;
-                    dstage[32] = vb;
-                    ca0 = na0; ca1 = na1; cb0 = nb0; cb1 = nb1;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[stage]);
                 }
+                sa = sa1; sb = sb1; sa1 = sa2; sb1 = sb2;
             }
             __syncthreads();   // consumers are done with this item; the beat tile may be rewritten
         }
@@ -184,41 +274,62 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
             const int m_begin = (int)(item % m_splits) * m_per_item;
             const int m_end = min(M, m_begin + m_per_item);
             const int64_t n0 = tile * BT;
+            load_beat_tile(Ytile, Y, N, T, YP, n0, warp, lane);
+            __syncthreads();   // tile complete
             for (int m = m_begin; m < m_end; ++m) {
                 double acc[4][8][2];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) acc[j][nt][0] = acc[j][nt][1] = 0.0;
+                // epilogue operand fetched early so its latency hides under the chunk loop
+                int st_epi = -1;
+                if (tid < BT && n0 + tid < N) st_epi = state_of[(n0 + tid) * M + m];
 
-                for (int kc = 0; kc < nrb; ++kc, ++it) {
-                    const int stage = it % STAGES;
-                    const uint32_t phase = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[stage], phase);
-                    // row blocks of this warp: rb = warp + 8 j; active iff kc <= rb < nrb
-                    if (warp + 24 >= kc) {   // otherwise nothing left for this warp in this chunk
-                        const double2* ds = reinterpret_cast<const double2*>(Dst + stage * D_STAGE_BYTES) + lane;
-                        double2 b[8];
+                if (nrb == MAX_NRB) {
+                    // T = 256 fast path.  This warp's row blocks rb_0 < rb_1 < rb_2 < rb_3 retire one after the
+                    // other as k advances, so the k-loop splits into phases with a FIXED active set.
+                    const int rb0 = warp, rb1 = 15 - warp, rb2 = 16 + warp, rb3 = 31 - warp;
+                    int kc = 0;
+#pragma unroll 1
+                    for (; kc <= rb0; ++kc, ++it) fast_chunk<0>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+#pragma unroll 1
+                    for (; kc <= rb1; ++kc, ++it) fast_chunk<1>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+#pragma unroll 1
+                    for (; kc <= rb2; ++kc, ++it) fast_chunk<2>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+#pragma unroll 1
+                    for (; kc <= rb3; ++kc, ++it) fast_chunk<3>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+#pragma unroll 1
+                    for (; kc < MAX_NRB; ++kc, ++it) fast_chunk<4>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+                } else {
+                    // generic path (T < 256): row blocks tested per chunk
+                    for (int kc = 0; kc < nrb; ++kc, ++it) {
+                        const int stage = it & (STAGES - 1);
+                        mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+                        if (31 - warp >= kc) {   // rb_3 = 31 - w is this warp's largest block
+                            const double2* ds = reinterpret_cast<const double2*>(Dst + stage * D_STAGE_BYTES) + lane;
+                            double2 b[8];
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) b[nt] = ds[nt * 32];
-                        const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane;
+                            for (int nt = 0; nt < 8; ++nt) b[nt] = ds[nt * 32];
+                            const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int rb = warp + 8 * j;
-                            if (rb >= kc && rb < nrb) {
-                                const double2 a = ws[(rb - kc) * 32];
+                            for (int j = 0; j < 4; ++j) {
+                                const int rb = (j & 1) ? (8 * j + 7 - warp) : (8 * j + warp);
+                                // a real branch (16 tensor instructions per body): predicated-off DMMAs would
+                                // still occupy the FP64 tensor pipe and forfeit the triangular saving
+                                if (rb >= kc && rb < nrb) {
+                                    const double2 a = ws[(rb - kc) * 32];
 #pragma unroll
-                                for (int nt = 0; nt < 8; ++nt) {
-                                    dmma884(acc[j][nt][0], acc[j][nt][1], a.x, b[nt].x);
-                                    dmma884(acc[j][nt][0], acc[j][nt][1], a.y, b[nt].y);
+                                    for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a.x, b[nt].x);
+#pragma unroll
+                                    for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a.y, b[nt].y);
                                 }
                             }
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[stage]);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[stage]);
                 }
-
                 // ---- epilogue: |z|^2 per beat ----
                 double* rbuf = red + (epi & 1) * (NCW * BT);
                 ++epi;
@@ -242,8 +353,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                         double s = 0.0;
 #pragma unroll
                         for (int w = 0; w < NCW; ++w) s += rbuf[w * BT + tid];
-                        const int st = state_of[n * M + m];
-                        q[n * M + m] = (st >= 0) ? (-0.5 * s - half_T_log2pi) : 0.0;
+                        q[n * M + m] = (st_epi >= 0) ? (-0.5 * s - half_T_log2pi) : 0.0;
                     }
                 }
             }
@@ -296,6 +406,47 @@ score_pairs_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
 // ------------------------------------------------------------------------------------------
 // SNR statistic: one warp per beat, looping clusters; smoothed means gathered through L1/L2
 // ------------------------------------------------------------------------------------------
+template <int NREG>   // NREG = ceil(T / 32) <= 8: the beat lives in registers
+__global__ void __launch_bounds__(256)
+snr_states_reg_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
+                      const int* __restrict__ snr_state_of, int M, double* __restrict__ snr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; n < N; n += wstride) {
+        double y[NREG];
+#pragma unroll
+        for (int k = 0; k < NREG; ++k) y[k] = (lane + 32 * k < T) ? Y[n * T + lane + 32 * k] : 0.0;
+        for (int m0 = 0; m0 < M; m0 += 2) {
+            // two clusters per step: 2 * NREG independent gathers in flight per lane
+            const int s0 = snr_state_of[n * M + m0];
+            const int s1 = (m0 + 1 < M) ? snr_state_of[n * M + m0 + 1] : -1;
+            const double* r0 = mu_sm + (int64_t)max(s0, 0) * T;
+            const double* r1 = mu_sm + (int64_t)max(s1, 0) * T;
+            double v0[NREG], v1[NREG];
+#pragma unroll
+            for (int k = 0; k < NREG; ++k) {
+                const int t = lane + 32 * k;
+                v0[k] = (s0 >= 0 && t < T) ? __ldg(r0 + t) : 0.0;
+                v1[k] = (s1 >= 0 && t < T) ? __ldg(r1 + t) : 0.0;
+            }
+            double sig0 = 0.0, noi0 = 0.0, sig1 = 0.0, noi1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < NREG; ++k) {
+                const bool in = lane + 32 * k < T;
+                const double d0 = in ? v0[k] - y[k] : 0.0, d1 = in ? v1[k] - y[k] : 0.0;
+                sig0 += v0[k] * v0[k]; noi0 += d0 * d0;
+                sig1 += v1[k] * v1[k]; noi1 += d1 * d1;
+            }
+            sig0 = warp_sum(sig0); noi0 = warp_sum(noi0);
+            sig1 = warp_sum(sig1); noi1 = warp_sum(noi1);
+            if (lane == 0) {
+                snr[n * M + m0] = (s0 >= 0) ? 10.0 * log10((sig0 + HGP_EPS) / (noi0 + HGP_EPS)) : 0.0;
+                if (m0 + 1 < M) snr[n * M + m0 + 1] = (s1 >= 0) ? 10.0 * log10((sig1 + HGP_EPS) / (noi1 + HGP_EPS)) : 0.0;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 snr_states_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
                   const int* __restrict__ snr_state_of, int M, double* __restrict__ snr) {
@@ -329,8 +480,10 @@ snr_states_kernel(const double* __restrict__ Y, int64_t N, int T, const double* 
 }  // namespace
 
 extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* mu, const double* Wpacked,
-                               const int* state_of, const int* factor_of_cluster, int M, double* q, void* stream) {
+                               const int* state_of, const int* factor_of_cluster, int M, double* q,
+                               const double* mu_sm, const int* snr_state_of, double* snr, void* stream) {
     HGP_REQUIRE(N >= 0 && M >= 0, "hgp_score_tiles: bad sizes");
+    HGP_REQUIRE(snr == nullptr || (mu_sm != nullptr && snr_state_of != nullptr), "hgp_score_tiles: snr needs mu_sm and snr_state_of");
     if (T <= 0 || T > 256) { hgp_set_error("hgp_score_tiles: need 0 < T <= 256 (got %d)", T); return HGP_E_UNSUPPORTED; }
     if (N == 0 || M == 0) return 0;
     static int n_sm = 0;
@@ -354,8 +507,9 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
     const int grid = (int)hgp_min64(n_items, n_sm);
     score_tiles_kernel<<<grid, TILE_THREADS, lay.total, (cudaStream_t)stream>>>(
         Y, N, T, mu, Wpacked, hgp_packed_factor_bytes(T) / 8, state_of, factor_of_cluster, M, m_per_item, m_splits,
-        n_items, q);
+        n_items, q, mu_sm, snr_state_of, snr);
     HGP_LAUNCH_CHECK("hgp_score_tiles");
+    if (snr) return hgp_snr_states(Y, N, T, mu_sm, snr_state_of, M, snr, stream);
     return 0;
 }
 
@@ -390,7 +544,13 @@ extern "C" int hgp_snr_states(const double* Y, int64_t N, int T, const double* m
         if (e != cudaSuccess) return hgp_status(e, "hgp_snr_states: smem attribute");
     }
     int blocks = (int)hgp_min64((N + warps - 1) / warps, 148 * 8);
-    snr_states_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
+    if (T <= 128) {
+        snr_states_reg_kernel<4><<<blocks, warps * 32, 0, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
+    } else if (T <= 256) {
+        snr_states_reg_kernel<8><<<blocks, warps * 32, 0, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
+    } else {
+        snr_states_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
+    }
     HGP_LAUNCH_CHECK("hgp_snr_states");
     return 0;
 }

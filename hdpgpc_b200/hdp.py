@@ -114,14 +114,20 @@ class LeadTables:
             self.pair_n = nz[:, 0].to(I32).contiguous()
             self.pair_m = nz[:, 1].to(I32).contiguous()
 
-    def score(self, out):
+    def score(self, out, snr_out=None):
+        """q (and, when snr_out is given, the SNR statistic) for this lead plane."""
         if self.use_tiles:
-            ops.score_tiles(self.Y, self.mu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out)
+            fuse = snr_out is not None and self.snr_state_of is not None
+            ops.score_tiles(self.Y, self.mu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out,
+                            mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of if fuse else None,
+                            snr_out=snr_out if fuse else None)
             if self.pair_n is not None:
                 ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m,
                                 out=out)
         else:
             ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, out=out)
+            if snr_out is not None and self.snr_state_of is not None:
+                self.snr(snr_out)
         return out
 
     def snr(self, out):
@@ -168,9 +174,7 @@ class EStepEngine:
     # -- pieces --
     def score_all(self):
         for ld, tb in enumerate(self.leads):
-            tb.score(self.q[ld])
-            if self.use_snr:
-                tb.snr(self.snr[ld])
+            tb.score(self.q[ld], self.snr[ld] if self.use_snr else None)
         return self.q, self.snr
 
     def responsibilities(self):

@@ -84,13 +84,14 @@ def emission_means(C, f, c_idx, f_idx):
     return mu
 
 
-def score_tiles(Y, mu, Wpacked, state_of, factor_of_cluster, out=None):
+def score_tiles(Y, mu, Wpacked, state_of, factor_of_cluster, out=None, mu_sm=None, snr_state_of=None, snr_out=None):
+    """Tensor-core tile scoring; with (mu_sm, snr_state_of, snr_out) the SNR statistic is fused in."""
     lib = _lib_ready()
     N, T = Y.shape
     M = state_of.shape[1]
     q = out if out is not None else torch.empty((N, M), dtype=F64, device=Y.device)
     check(lib.hgp_score_tiles(ptr(Y), N, T, ptr(mu), ptr(Wpacked), ptr(state_of), ptr(factor_of_cluster), M, ptr(q),
-                              stream_ptr()), "hgp_score_tiles")
+                              ptr(mu_sm), ptr(snr_state_of), ptr(snr_out), stream_ptr()), "hgp_score_tiles")
     return q
 
 

@@ -71,12 +71,15 @@ int hgp_pack_factors(const double* W, int64_t F, int T, double* Wpacked, void* s
  *     q[n*M + m] = -0.5 * | W_f (Y[n] - mu[s]) |^2 - 0.5 * T * log(2 pi)        (no log-det)
  *
  * hgp_score_tiles: f = factor_of_cluster[m]; all beats, W in packed form; tensor-core (DMMA) path.
+ *                  When snr != NULL the SNR lead statistic of hgp_snr_states (below) is fused into the
+ *                  same pass (the producer warps that stage y - mu also accumulate it).
  * hgp_score_pairs: explicit list of (n, m) pairs with f = factor_of_state[s]; W in plain form;
  *                  used for the states whose covariance differs from the cluster's shared one
  *                  (per-state Sigma_i when estimation_limit=None, the `first` jitter) and as the
  *                  general path when every state has its own factor. */
 int hgp_score_tiles(const double* Y, int64_t N, int T, const double* mu, const double* Wpacked,
-                    const int* state_of, const int* factor_of_cluster, int M, double* q, void* stream);
+                    const int* state_of, const int* factor_of_cluster, int M, double* q,
+                    const double* mu_sm, const int* snr_state_of, double* snr, void* stream);
 int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const double* W,
                     const int* state_of, const int* factor_of_state, int M,
                     const int* pair_n, const int* pair_m, int64_t n_pairs, double* q, void* stream);
