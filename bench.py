@@ -160,6 +160,9 @@ def measure_fp64_peak(torch, seconds=1.5):
 
 
 def run_ours(args):
+    if os.environ.get("HGP_BENCH_WATCHDOG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["HGP_BENCH_WATCHDOG"]), exit=True)
     import torch
     import torch.distributed as dist
     import hdpgpc_b200 as hb
@@ -180,6 +183,13 @@ def run_ours(args):
     Y_host = wl["Y"].cpu().pin_memory()                      # e2e leg: beats live in pinned host memory
     eng = synthetic.build_engine(wl)
     assert all(tb.use_tiles for tb in eng.leads)
+
+    if world > 1:   # a size mismatch in a broadcast hangs NCCL silently: check once, loudly
+        sz = torch.tensor([tb.Wpacked.numel() for tb in eng.leads], dtype=torch.int64, device="cuda")
+        allsz = [torch.empty_like(sz) for _ in range(world)]
+        dist.all_gather(allsz, sz)
+        if any(not torch.equal(a, sz) for a in allsz):
+            raise hb.HgpError(f"factor tables differ across ranks: {[a.tolist() for a in allsz]}")
 
     # shared factors are broadcast from rank 0 each sweep when sharded (cluster parameters broadcast)
     def broadcast_tables():

@@ -30,6 +30,9 @@ PROTOTYPES = {
                               _c.POINTER(_int), _p]),
     "hgp_suffstats_workspace_bytes": (_i64, [_i64, _int]),
     "hgp_suffstats": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _i64, _p]),
+    "hgp_qlat_workspace_bytes": (_i64, [_i64, _int]),
+    "hgp_qlat_batched": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _int, _p, _p, _p, _i64, _p]),
+    "hgp_gemm_batched": (_int, [_p, _p, _p, _p, _p, _i64, _int, _int, _int, _p]),
     "hgp_emission_means": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
 }
 

@@ -16,6 +16,11 @@
 extern std::atomic<int64_t> g_hgp_launches;
 void hgp_set_error(const char* fmt, ...);
 
+// chol of sc[f] * Sigma[src_idx[f]] (+ add_diag[f] I); src_idx / src_scale may be NULL
+int hgp_internal_chol(const double* Sigma, const int* src_idx, const double* src_scale, int64_t F, int T,
+                      const double* add_diag, double jitter_scale, double* Lfac, double* logdet, int* info,
+                      void* stream);
+
 static inline int hgp_status(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return 0;
     hgp_set_error("%s: %s", what, cudaGetErrorString(e));

@@ -23,7 +23,8 @@ __global__ void pack_leads_kernel(const double* __restrict__ Y, int64_t N, int T
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS)
-chol_kernel(const double* __restrict__ Sigma, int T, const double* __restrict__ add_diag, double jitter_scale,
+chol_kernel(const double* __restrict__ Sigma, const int* __restrict__ src_idx, const double* __restrict__ src_scale,
+            int T, const double* __restrict__ add_diag, double jitter_scale,
             double* __restrict__ Lfac, double* __restrict__ logdet, int* __restrict__ info) {
     extern __shared__ double smem[];
     double* Dk = smem;                       // [NB][NB+1]
@@ -33,14 +34,15 @@ chol_kernel(const double* __restrict__ Sigma, int T, const double* __restrict__ 
     __shared__ int s_info;
 
     const int64_t f = blockIdx.x;
-    const double* S = Sigma + f * (int64_t)T * T;
+    const double* S = Sigma + (src_idx ? (int64_t)src_idx[f] : f) * (int64_t)T * T;
+    const double sc = src_scale ? src_scale[f] : 1.0;     // matrix = sc * Sigma[src]
     double* A = Lfac + f * (int64_t)T * T;
     const int tid = threadIdx.x;
     const double add = add_diag ? add_diag[f] : 0.0;
 
     // diag mean of (S + add I)
     double part = 0.0;
-    for (int i = tid; i < T; i += CHOL_THREADS) part += fabs(S[(int64_t)i * T + i] + add);
+    for (int i = tid; i < T; i += CHOL_THREADS) part += fabs(S[(int64_t)i * T + i] * sc + add);
     part = warp_sum(part);
     if ((tid & 31) == 0) s_red[tid >> 5] = part;
     if (tid == 0) s_info = 0;
@@ -56,8 +58,8 @@ chol_kernel(const double* __restrict__ Sigma, int T, const double* __restrict__ 
         int i = idx / T, j = idx % T;
         double v;
         if (j > i) v = 0.0;
-        else if (j == i) v = (S[idx] + add) + jit;   // sym() leaves the diagonal unchanged
-        else v = 0.5 * (S[idx] + S[(int64_t)j * T + i]);
+        else if (j == i) v = (S[idx] * sc + add) + jit;   // sym() leaves the diagonal unchanged
+        else v = 0.5 * (S[idx] * sc + S[(int64_t)j * T + i] * sc);
         A[idx] = v;
     }
     __syncthreads();
@@ -239,8 +241,9 @@ extern "C" int hgp_pack_leads(const double* Y_ntl, int64_t N, int T, int L, doub
     return 0;
 }
 
-extern "C" int hgp_chol_batched(const double* Sigma, int64_t F, int T, const double* add_diag, double jitter_scale,
-                                double* Lfac, double* logdet, int* info, void* stream) {
+int hgp_internal_chol(const double* Sigma, const int* src_idx, const double* src_scale, int64_t F, int T,
+                      const double* add_diag, double jitter_scale, double* Lfac, double* logdet, int* info,
+                      void* stream) {
     HGP_REQUIRE(F >= 0 && T > 0 && T <= 1024, "hgp_chol_batched: need 0 < T <= 1024");
     if (F == 0) return 0;
     size_t smem = sizeof(double) * (NB * (NB + 1) + (size_t)T * (NB + 1));
@@ -248,9 +251,15 @@ extern "C" int hgp_chol_batched(const double* Sigma, int64_t F, int T, const dou
         cudaError_t e = cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return hgp_status(e, "hgp_chol_batched: smem attribute");
     }
-    chol_kernel<<<(unsigned)F, CHOL_THREADS, smem, (cudaStream_t)stream>>>(Sigma, T, add_diag, jitter_scale, Lfac, logdet, info);
+    chol_kernel<<<(unsigned)F, CHOL_THREADS, smem, (cudaStream_t)stream>>>(Sigma, src_idx, src_scale, T, add_diag,
+                                                                          jitter_scale, Lfac, logdet, info);
     HGP_LAUNCH_CHECK("hgp_chol_batched");
     return 0;
+}
+
+extern "C" int hgp_chol_batched(const double* Sigma, int64_t F, int T, const double* add_diag, double jitter_scale,
+                                double* Lfac, double* logdet, int* info, void* stream) {
+    return hgp_internal_chol(Sigma, nullptr, nullptr, F, T, add_diag, jitter_scale, Lfac, logdet, info, stream);
 }
 
 extern "C" int hgp_tri_inverse_batched(const double* Lfac, int64_t F, int T, double* W, void* stream) {

@@ -2,6 +2,7 @@
 // GEMV: one CTA per state, one warp per output row, coalesced row reads (HBM-bound: T*T*8 bytes
 // per state when every state has its own C).
 #include "hgp_common.cuh"
+#include "hgp_gemm.cuh"
 
 namespace {
 
@@ -24,6 +25,53 @@ emission_means_kernel(const double* __restrict__ C, const double* __restrict__ f
     }
 }
 
+
+// Latent-transition score, final step per member: r = f_cur - A f_prev, z = W r (W = chol(Gamma)^{-1}),
+// out = -0.5 (|z|^2 + trace) - 0.5 T log 2 pi with trace = sum of the GEMM tile partials (fixed order).
+__global__ void __launch_bounds__(256)
+qlat_finish_kernel(const double* __restrict__ A, const int* __restrict__ A_idx, const double* __restrict__ W,
+                   const double* __restrict__ fmean, const int* __restrict__ fprev_idx,
+                   const int* __restrict__ fcur_idx, const double* __restrict__ partial, int ntile2, int T,
+                   const int* __restrict__ info, double* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* fp = sm;          // f_prev
+    double* r = sm + T;       // residual
+    __shared__ double s_red[8];
+    const int64_t j = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* Aj = A + (int64_t)A_idx[j] * T * T;
+    const double* Wj = W + j * (int64_t)T * T;
+    const double* fprev = fmean + (int64_t)fprev_idx[j] * T;
+    const double* fcur = fmean + (int64_t)fcur_idx[j] * T;
+    for (int t = tid; t < T; t += 256) fp[t] = fprev[t];
+    __syncthreads();
+    for (int row = warp; row < T; row += 8) {
+        const double* ar = Aj + (int64_t)row * T;
+        double acc = 0.0;
+        for (int k = lane; k < T; k += 32) acc += ar[k] * fp[k];
+        acc = warp_sum(acc);
+        if (lane == 0) r[row] = fcur[row] - acc;
+    }
+    __syncthreads();
+    double mah = 0.0;
+    for (int row = warp; row < T; row += 8) {
+        const double* wr = Wj + (int64_t)row * T;
+        double acc = 0.0;
+        for (int k = lane; k <= row; k += 32) acc += wr[k] * r[k];
+        acc = warp_sum(acc);
+        mah += acc * acc;      // identical in every lane
+    }
+    if (lane == 0) s_red[warp] = mah;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int w = 0; w < 8; ++w) m += s_red[w];
+        double tr = 0.0;
+        for (int t = 0; t < ntile2; ++t) tr += partial[j * ntile2 + t];
+        out[j] = (info[j] == 0) ? (-0.5 * (m + tr) - 0.5 * (double)T * HGP_LOG2PI) : nan("");
+    }
+}
+
 }  // namespace
 
 extern "C" int hgp_emission_means(const double* C, const double* f, const int* c_idx, const int* f_idx, int64_t S,
@@ -32,5 +80,66 @@ extern "C" int hgp_emission_means(const double* C, const double* f, const int* c
     if (S == 0) return 0;
     emission_means_kernel<<<(unsigned)S, 256, sizeof(double) * T, (cudaStream_t)stream>>>(C, f, c_idx, f_idx, T, mu);
     HGP_LAUNCH_CHECK("hgp_emission_means");
+    return 0;
+}
+
+extern "C" int hgp_gemm_batched(const double* A, const int* ia, const double* B, const int* ib, double* C, int64_t J,
+                                int T, int lowerA, int transA, void* stream) {
+    HGP_REQUIRE(J >= 0 && T > 0 && T <= 4096, "hgp_gemm_batched: bad sizes");
+    if (J == 0) return 0;
+    const int nt = (T + hgp::GT - 1) / hgp::GT;
+    const int64_t st = (int64_t)T * T;
+    for (int64_t j0 = 0; j0 < J; j0 += 65535) {
+        const int64_t jb = hgp_min64(65535, J - j0);
+        dim3 grid(nt * nt, (unsigned)jb);
+        hgp::gemm_tile_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            ia ? A : A + j0 * st, ia ? ia + j0 : nullptr, st, lowerA, transA, ib ? B : B + j0 * st, ib ? ib + j0 : nullptr,
+            st, C + j0 * st, st, nullptr, 0, nullptr, T);
+        HGP_LAUNCH_CHECK("hgp_gemm_batched");
+    }
+    return 0;
+}
+
+static int64_t qlat_sub_batch(int64_t J) { return hgp_min64(J, 256); }
+
+extern "C" int64_t hgp_qlat_workspace_bytes(int64_t J, int T) {
+    const int64_t jb = qlat_sub_batch(J);
+    const int64_t nt = (T + hgp::GT - 1) / hgp::GT;
+    return jb * (2 * (int64_t)T * T + nt * nt) * (int64_t)sizeof(double) + 256;
+}
+
+extern "C" int hgp_qlat_batched(const double* A, const double* Gamma, const double* P, const double* fmean,
+                                const int* A_idx, const int* G_idx, const int* P_idx, const int* fprev_idx,
+                                const int* fcur_idx, const double* gamma_scale, int64_t J, int T, double* out,
+                                int* info, void* workspace, int64_t workspace_bytes, void* stream) {
+    HGP_REQUIRE(J >= 0 && T > 0 && T <= 1024, "hgp_qlat_batched: need 0 < T <= 1024");
+    if (J == 0) return 0;
+    if (workspace_bytes < hgp_qlat_workspace_bytes(J, T)) { hgp_set_error("hgp_qlat_batched: workspace too small"); return HGP_E_WORKSPACE; }
+    const int64_t jbmax = qlat_sub_batch(J);
+    const int nt = (T + hgp::GT - 1) / hgp::GT;
+    const int64_t st = (int64_t)T * T;
+    double* W1 = reinterpret_cast<double*>(workspace);      // chol(Gamma), later X = W A
+    double* W2 = W1 + jbmax * st;                           // W = chol(Gamma)^{-1}
+    double* part = W2 + jbmax * st;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t j0 = 0; j0 < J; j0 += jbmax) {
+        const int64_t jb = hgp_min64(jbmax, J - j0);
+        int rc = hgp_internal_chol(Gamma, G_idx + j0, gamma_scale ? gamma_scale + j0 : nullptr, jb, T, nullptr, 1e-8, W1,
+                                   nullptr, info + j0, stream);
+        if (rc) return rc;
+        rc = hgp_tri_inverse_batched(W1, jb, T, W2, stream);
+        if (rc) return rc;
+        dim3 grid(nt * nt, (unsigned)jb);
+        // X = W A   (W lower triangular)
+        hgp::gemm_tile_kernel<0><<<grid, 256, 0, s>>>(W2, nullptr, st, 1, 0, A, A_idx + j0, st, W1, st, nullptr, 0, nullptr, T);
+        HGP_LAUNCH_CHECK("hgp_qlat_batched: X = W A");
+        // partial = sum (X P) .* X
+        hgp::gemm_tile_kernel<1><<<grid, 256, 0, s>>>(W1, nullptr, st, 0, 0, P, P_idx + j0, st, nullptr, 0, W1, st, part, T);
+        HGP_LAUNCH_CHECK("hgp_qlat_batched: trace");
+        qlat_finish_kernel<<<(unsigned)jb, 256, 2 * sizeof(double) * T, s>>>(A, A_idx + j0, W2, fmean, fprev_idx + j0,
+                                                                           fcur_idx + j0, part, nt * nt, T, info + j0,
+                                                                           out + j0);
+        HGP_LAUNCH_CHECK("hgp_qlat_batched: finish");
+    }
     return 0;
 }

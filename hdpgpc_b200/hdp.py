@@ -134,6 +134,40 @@ class LeadTables:
         return ops.snr_states(self.Y, self.mu_sm, self.snr_state_of, out=out)
 
 
+def sharded_hmm_exchange(smooth, K, rank, world, group, device):
+    """Exact HMM smoothing over rank-sharded beats.  Every rank scans its slice from
+    a guessed boundary message; the boundary messages (2K doubles per rank: alpha of the slice's last
+    beat, beta (.) e of its first beat) are all-gathered; slices whose incoming message changed are
+    scanned again; repeat until no boundary moves BITWISE.  The recursion is a deterministic function of
+    the incoming message, so the fixed point equals the sequential scan bit for bit.
+
+    smooth(boundary_in[2K], has_prev, has_next) -> result with .boundary_out[2K] (device tensor)."""
+    dist = torch.distributed
+    has_prev, has_next = rank > 0, rank < world - 1
+    bin_ = torch.empty(2 * K, dtype=F64, device=device)
+    bin_[:K] = 1.0 / K                     # guess for alpha of the previous rank's last beat
+    bin_[K:] = 1.0                         # guess for (beta . e) of the next rank's first beat
+    gathered_flat = torch.empty(world * 2 * K, dtype=F64, device=device)   # 1-D: accepted by nccl and gloo alike
+    gathered = gathered_flat.view(world, 2 * K)
+    rounds = 0
+    while True:
+        hm = smooth(bin_, has_prev, has_next)
+        dist.all_gather_into_tensor(gathered_flat, hm.boundary_out.contiguous(), group=group)
+        new_in = bin_.clone()
+        if has_prev:
+            new_in[:K] = gathered[rank - 1, :K]
+        if has_next:
+            new_in[K:] = gathered[rank + 1, K:]
+        changed = (new_in.view(torch.int64) != bin_.view(torch.int64)).any().to(torch.int32).reshape(1)
+        dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=group)
+        rounds += 1
+        if int(changed) == 0:
+            return hm, rounds
+        bin_ = new_in
+        if rounds > world + 2:
+            raise HgpError("sharded HMM boundary exchange did not converge")
+
+
 class EStepEngine:
     """One E-step sweep over a (slice of a) beat sequence:  q[N,M,L] -> lead weights -> q-bar ->
     HMM forward/backward -> arg-max resp / respPair -> N_m, startStateCount, transStateCount, Q_em
@@ -188,36 +222,10 @@ class EStepEngine:
         return qbar, e, w, hm
 
     def _hmm_sharded(self, e):
-        """Exact HMM smoothing over rank-sharded beats: every rank scans its slice from a guessed
-        boundary, the boundary messages (2K doubles per rank) are all-gathered, and slices whose
-        incoming message changed are re-scanned; repeat until no boundary moves (bitwise)."""
-        dist = torch.distributed
-        K = self.M
-        G, r = self.world, self.rank
-        has_prev, has_next = r > 0, r < G - 1
-        bin_ = torch.empty(2 * K, dtype=F64, device=self.device)
-        bin_[:K] = 1.0 / K                     # guess for alpha of the previous rank's last beat
-        bin_[K:] = 1.0                         # guess for (beta . e) of the next rank's first beat
-        gathered = torch.empty((G, 2 * K), dtype=F64, device=self.device)
-        hm = None
-        rounds = 0
-        while True:
-            hm = ops.hmm_smooth(e, self.pi, self.PiT, self.Pi, self.Pc, boundary_in=bin_, has_prev=has_prev,
-                                has_next=has_next, workspace=self._hmm_ws)
-            dist.all_gather_into_tensor(gathered, hm.boundary_out, group=self.group)
-            new_in = bin_.clone()
-            if has_prev:
-                new_in[:K] = gathered[r - 1, :K]
-            if has_next:
-                new_in[K:] = gathered[r + 1, K:]
-            changed = (new_in.view(torch.int64) != bin_.view(torch.int64)).any().to(torch.int32)
-            dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=self.group)
-            rounds += 1
-            if int(changed) == 0:
-                break
-            bin_ = new_in
-            if rounds > G + 2:
-                raise HgpError("sharded HMM boundary exchange did not converge")
+        smooth = lambda bin_, has_prev, has_next: ops.hmm_smooth(
+            e, self.pi, self.PiT, self.Pi, self.Pc, boundary_in=bin_, has_prev=has_prev, has_next=has_next,
+            workspace=self._hmm_ws)
+        hm, rounds = sharded_hmm_exchange(smooth, self.M, self.rank, self.world, self.group, self.device)
         self.boundary_rounds = rounds
         return hm
 

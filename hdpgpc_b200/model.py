@@ -203,3 +203,34 @@ class GPI_model:
         q = ops.score_pairs(Y, mu, tb["W"], torch.tensor([[s]], dtype=torch.int32, device=dev),
                             torch.from_numpy(fos).to(dev))
         return q[0, 0]
+
+    def compute_q_lat_all(self, x_trains, h_ini=1.0):
+        """GPI_model.compute_q_lat_all (GPI_model.py:549-559) -> log_lat_error (:288-323): per member j the
+        latent transition score of its smoothed state under (A, Gamma) of step j+1; zero elsewhere."""
+        n = x_trains.shape[0] if hasattr(x_trains, "shape") else len(x_trains)
+        out = torch.zeros(n, dtype=F64, device=self.device)
+        if self.N == 0 or self.Gamma is None or not bool(torch.any(self.Gamma[-1] != 0)):
+            return out
+        nG = self.Gamma.shape[0]
+        J = self.N
+        a_idx = np.empty(J, dtype=np.int32); p_idx = np.empty(J, dtype=np.int32)
+        fp_idx = np.empty(J, dtype=np.int32); fc_idx = np.empty(J, dtype=np.int32)
+        scale = np.ones(J)
+        for j in range(J):
+            if j == 0:
+                p_idx[j] = fp_idx[j] = 1
+                a_idx[j] = nG - 1
+                scale[j] = h_ini
+            else:
+                p_idx[j] = fp_idx[j] = j
+                a_idx[j] = j + 1 if j + 1 < nG else nG - 1
+            fc_idx[j] = j + 1
+        dev = self.device
+        t = lambda a, dt=torch.int32: torch.from_numpy(a).to(dev).to(dt)
+        vals, info = ops.qlat_batched(self.A, self.Gamma, self.cov_f_sm, self.f_star_sm, t(a_idx), t(a_idx), t(p_idx),
+                                      t(fp_idx), t(fc_idx), gamma_scale=t(scale, F64))
+        bad = torch.nonzero(info).flatten()
+        if bad.numel():
+            raise LinAlgError(f"linalg.cholesky: Gamma of member {int(bad[0])} is not positive-definite")
+        out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals
+        return out

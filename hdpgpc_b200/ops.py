@@ -173,3 +173,33 @@ def suffstats(z, zpair, qbar, is_first_slice=True, workspace=None):
     check(lib.hgp_suffstats(ptr(z), ptr(zpair), ptr(qbar), N, K, int(is_first_slice), ptr(Nm), ptr(trans), ptr(start),
                             ptr(Qem), ptr(workspace), workspace.numel(), stream_ptr()), "hgp_suffstats")
     return Nm, trans, start, Qem, packed
+
+
+def gemm_batched(A, B, ia=None, ib=None, lowerA=False, transA=False):
+    """C[j] = op(A[ia[j]]) @ B[ib[j]] for stacks of T x T matrices (FP64 tensor cores)."""
+    lib = _lib_ready()
+    A = _dev(A).contiguous()
+    B = _dev(B).contiguous()
+    T = A.shape[-1]
+    J = ia.numel() if ia is not None else (ib.numel() if ib is not None else A.shape[0])
+    C = torch.empty((J, T, T), dtype=F64, device=A.device)
+    check(lib.hgp_gemm_batched(ptr(A), ptr(ia), ptr(B), ptr(ib), ptr(C), J, T, int(lowerA), int(transA), stream_ptr()),
+          "hgp_gemm_batched")
+    return C
+
+
+def qlat_batched(A, Gamma, P, fmean, A_idx, G_idx, P_idx, fprev_idx, fcur_idx, gamma_scale=None, workspace=None):
+    """Latent-transition scores (GPI_model.log_lat_error) for J members.  Returns (out [J], info [J])."""
+    lib = _lib_ready()
+    J = A_idx.numel()
+    T = fmean.shape[1]
+    dev = fmean.device
+    out = torch.empty(J, dtype=F64, device=dev)
+    info = torch.zeros(J, dtype=I32, device=dev)
+    need = lib.hgp_qlat_workspace_bytes(J, T)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib.hgp_qlat_batched(ptr(A), ptr(Gamma), ptr(P), ptr(fmean), ptr(A_idx), ptr(G_idx), ptr(P_idx),
+                               ptr(fprev_idx), ptr(fcur_idx), ptr(gamma_scale), J, T, ptr(out), ptr(info),
+                               ptr(workspace), workspace.numel(), stream_ptr()), "hgp_qlat_batched")
+    return out, info

@@ -121,15 +121,16 @@ def make_workload(N, T=256, L=2, M=64, seed=1234, device="cpu", n_offset=0, N_to
         st_of = state_of
         if jitter_first:
             # `first` rule (GPI_model.py:527-529): the first member of each cluster is scored under
-            # Sigma + 1e-2 mean(diag Sigma_0) I -> a duplicate state row with its own factor
+            # Sigma + 1e-2 mean(diag Sigma_0) I -> a duplicate state row whose factor carries the jitter.
+            # Every rank holds the same 2M factors (M shared + M jittered) so they can be broadcast as one table.
+            Sig = torch.cat([Sig, Sig], dim=0)
+            add = torch.cat([add, 1e-2 * 0.5 * torch.ones(M, dtype=F64, device=dev)])
             mem_first = torch.nonzero(first_mask & (counts_before[lab_s] == 0)).flatten()
             kf = mem_first.numel()
             if kf:
                 cl = lab_s[mem_first]
                 mu = torch.cat([mu, f[mem_first]], dim=0)
-                Sig = torch.cat([Sig, Sig[cl]], dim=0)
-                add = torch.cat([add, 1e-2 * 0.5 * torch.ones(kf, dtype=F64, device=dev)])
-                fos = torch.cat([fos, (M + torch.arange(kf, device=dev)).to(torch.int32)])
+                fos = torch.cat([fos, (M + cl).to(torch.int32)])
                 st_of = state_of.clone()
                 st_of[mem_first, cl] = (S + torch.arange(kf, device=dev)).to(torch.int32)
         out_leads.append(dict(mu=mu, Sigma=Sig, add_diag=add, factor_of_state=fos, state_of=st_of,

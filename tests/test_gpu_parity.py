@@ -96,6 +96,57 @@ def test_compute_sq_err_all_vs_reference(golden, name):
             assert rel(qn, z["q_new"][:4, m, ld]) < TOL
 
 
+@pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2"])
+def test_compute_q_lat_all_vs_reference(golden, name):
+    import hdpgpc_b200 as hb
+    z = golden(name)
+    M, L = int(z["M"]), int(z["L"])
+    N = z["data"].shape[0]
+    xt = np.repeat(z["x_basis"][None], N, axis=0)
+    for ld in range(L):
+        for m in range(M):
+            gp = hb.GPI_model.from_dump(z, f"gp_{ld}_{m}_")
+            ql = gp.compute_q_lat_all(xt)
+            assert ql.shape == (N,)
+            assert rel(ql, z["q_lat_all"][:, m, ld]) < TOL
+
+
+@pytest.mark.parametrize("T", [5, 64, 90, 200, 256])
+def test_gemm_and_qlat_vs_oracle(T):
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(T)
+    J = 5
+    A = rng.standard_normal((3, T, T)) * 0.1 + np.eye(T)
+    B = rng.standard_normal((4, T, T))
+    ia = np.array([0, 2, 1, 1, 0], dtype=np.int32); ib = np.array([3, 3, 0, 1, 2], dtype=np.int32)
+    C = ops.gemm_batched(cu(A), cu(B), cu(ia, torch.int32), cu(ib, torch.int32))
+    ref = np.stack([A[i] @ B[j] for i, j in zip(ia, ib)])
+    assert np.max(np.abs(C.cpu().numpy() - ref)) < 1e-11 * np.max(np.abs(ref))
+    Ct = ops.gemm_batched(cu(A), cu(B), cu(ia, torch.int32), cu(ib, torch.int32), transA=True)
+    ref = np.stack([A[i].T @ B[j] for i, j in zip(ia, ib)])
+    assert np.max(np.abs(Ct.cpu().numpy() - ref)) < 1e-11 * np.max(np.abs(ref))
+    Lw = np.tril(A)
+    Cl = ops.gemm_batched(cu(Lw), cu(B), cu(ia, torch.int32), cu(ib, torch.int32), lowerA=True)
+    ref = np.stack([Lw[i] @ B[j] for i, j in zip(ia, ib)])
+    assert np.max(np.abs(Cl.cpu().numpy() - ref)) < 1e-11 * np.max(np.abs(ref))
+    # q_lat against the oracle's formula on random SPD inputs
+    Gam = random_spd(rng, 3, T, cond=1e4) * 0.01
+    P = random_spd(rng, 4, T, cond=1e3)
+    f = rng.standard_normal((6, T)) * 10
+    pi_ = np.array([1, 0, 3, 2, 2], dtype=np.int32); fp = np.array([0, 1, 2, 3, 4], dtype=np.int32); fc = fp + 1
+    sc = np.array([1.0, 0.5, 1.0, 2.0, 1.0])
+    out, info = ops.qlat_batched(cu(A), cu(Gam), cu(P), cu(f), cu(ia, torch.int32), cu(ia, torch.int32),
+                                 cu(pi_, torch.int32), cu(fp, torch.int32), cu(fc, torch.int32), gamma_scale=cu(sc))
+    assert int(torch.count_nonzero(info)) == 0
+    for j in range(J):
+        r = f[fc[j]] - A[ia[j]] @ f[fp[j]]
+        Lg = O.chol_spd(Gam[ia[j]] * sc[j])
+        mah = np.sum(r * O.cho_solve(Lg, r))
+        tr = np.trace(A[ia[j]].T @ O.cho_solve(Lg, A[ia[j]]) @ P[pi_[j]])
+        refv = -0.5 * (mah + tr) - 0.5 * T * O.LOG2PI
+        assert abs(float(out[j]) - refv) < TOL * abs(refv)
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
