@@ -33,6 +33,10 @@ PROTOTYPES = {
     "hgp_qlat_workspace_bytes": (_i64, [_i64, _int]),
     "hgp_qlat_batched": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _int, _p, _p, _p, _i64, _p]),
     "hgp_gemm_batched": (_int, [_p, _p, _p, _p, _p, _i64, _int, _int, _int, _p]),
+    "hgp_chain_desc_bytes": (_i64, []),
+    "hgp_chain_work_doubles": (_i64, [_int]),
+    "hgp_chain_run": (_int, [_p, _int, _int, _p]),
+    "hgp_la_op": (_int, [_int, _p, _p, _p, _p, _int, _p, _p]),
     "hgp_emission_means": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
 }
 
@@ -82,3 +86,12 @@ def ptr(t):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+class ChainDesc(ctypes.Structure):
+    """Mirror of hgp_chain_desc (include/hdpgpc_b200.h)."""
+    _fields_ = ([("n_members", _int), ("first_is_prior", _int), ("annealing", _int), ("estimation_limit", _int),
+                 ("r_first", _dbl), ("member_beats", _p), ("Y", _p)] +
+                [(n, _p) for n in ("f_star", "f_star_sm", "cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma",
+                                   "int_m_mean", "int_m_r_cov", "int_scale", "int_n0",
+                                   "obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0", "work", "piv", "status")])

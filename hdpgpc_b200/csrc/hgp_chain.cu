@@ -1,0 +1,260 @@
+// Cluster propagation ("M-step" chain replay) on the device: reference GPI_model.full_pass_weighted
+// (GPI_model.py:377-406) = per member  include_weighted_sample -> IterativeGaussianProcess.posterior (Kalman
+// update in Joseph form, GPI.py:72-151)  +  backwards_pair -> backward_notrange (2-step RTS smoother,
+// GPI.py:272-300)  +  bayesian_new_params -> matrix_normal_inv_wishart.posterior (MNIW 1-step update,
+// GPI_model.py:966-1101, :1300-1344),  then backwards -> backward (full RTS pass, GPI.py:240-270).
+//
+// The chain is sequential in its members (parameters of step k depend on the smoothed state of step k-1), so
+// the parallelism is (cluster, lead) chains x dense T x T algebra: ONE persistent CTA walks one chain through
+// all of its steps with the CTA-level routines of hgp_cta_la.cuh (tensor-core GEMMs, blocked factorizations);
+// the ~12 T x T temporaries and the state histories stay in L2/HBM, nothing returns to the host between steps.
+// Shared basis grid only (x_train == x_basis: every shipped configuration); dynamic model (Gamma != 0).
+#include "hgp_common.cuh"
+#include "hgp_cta_la.cuh"
+
+using namespace hgp;
+
+namespace {
+
+struct Mniw {
+    double* m_mean;
+    double* m_r_cov;
+    double* scale;
+    double* n0;     // device scalar
+};
+
+// matrix_normal_inv_wishart.posterior for n_k = 1 with zero covariance terms and sse_matrix = I
+// (GPI_model.py:1300-1344).  W0..W3: T x T scratch.  Returns chol info (0 = ok).
+__device__ int mniw_posterior_one(Mniw d, const double* y1, const double* y2, int T, double* W0, double* W1, double* W2,
+                                  double* W3, double* vec, LaSmem& sm) {
+    const int n = T * T;
+    const double n0 = *d.n0;
+    // Ls = chol(sym(m_r_cov) + 1e-2 * max(mean|diag scale|, eps) I)
+    const double jitter = 1e-2 * fmax(la_mean_abs_diag(d.scale, T, sm), HGP_EPS);
+    la_copy(W0, d.m_r_cov, n);
+    la_symmetrize(W0, jitter, T);
+    int info = la_chol(W0, T, sm);
+    // Sinv = cholesky_solve(I, Ls)
+    la_set_identity(W1, 1.0, T);
+    la_trsm_lower(W0, W1, T, sm);
+    la_trsm_lower_trans(W0, W1, T, sm);                 // W1 = Sinv
+    // S2 = y2 y2^T + Sinv ; S1 = y1 y2^T + m_mean Sinv
+    la_gemm(W2, d.m_mean, 0, W1, 0, T, 1.0, 0.0, nullptr, sm);   // W2 = m_mean Sinv
+    la_rank1(W2, 1.0, y1, y2, T);                               // W2 = S1
+    la_rank1(W1, 1.0, y2, y2, T);                               // W1 = S2
+    // part_mean = cholesky_solve(S1^T, chol(sym(S2) + 1e-8 I))^T
+    la_copy(W0, W1, n);
+    la_symmetrize(W0, 1e-8, T);
+    int info2 = la_chol(W0, T, sm);
+    la_transpose(W3, W2, T);
+    la_trsm_lower(W0, W3, T, sm);
+    la_trsm_lower_trans(W0, W3, T, sm);                 // W3 = part_mean^T
+    // new_m_mean = ((n0 - 2) m_mean + part_mean) / (n0 + 1 - 2) ; new_scale = ((n0 - 2) scale + e e^T) / (n0 - 1)
+    const double a = (n0 - 2.0), den = (n0 + 1.0) - 2.0;
+    for (int i = threadIdx.x; i < n; i += LA_THREADS) {
+        const int r = i / T, c = i % T;
+        d.m_mean[i] = (a * d.m_mean[i] + W3[(int64_t)c * T + r]) / den;
+        const double e_r = y1[r] - y2[r], e_c = y1[c] - y2[c];
+        d.scale[i] = (a * d.scale[i] + e_r * e_c) / den;
+        d.m_r_cov[i] = W1[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *d.n0 = n0 + 1.0;
+    __syncthreads();
+    (void)vec;
+    return info ? info : info2;
+}
+
+}  // namespace
+
+namespace {
+
+__global__ void __launch_bounds__(LA_THREADS)
+chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
+    __shared__ LaSmem sm;
+    const hgp_chain_desc d = descs[blockIdx.x];
+    const int n = T * T;
+    const int64_t tt = (int64_t)T * T;
+    double* W0 = d.work;
+    double* W1 = W0 + tt; double* W2 = W1 + tt; double* W3 = W2 + tt;
+    double* W4 = W3 + tt; double* W5 = W4 + tt; double* W6 = W5 + tt; double* W7 = W6 + tt;
+    double* v0 = W7 + tt; double* v1 = v0 + T; double* v2 = v1 + T;
+    Mniw mi{d.int_m_mean, d.int_m_r_cov, d.int_scale, d.int_n0};
+    Mniw mo{d.obs_m_mean, d.obs_m_r_cov, d.obs_scale, d.obs_n0};
+    int fail = 0;
+    int N = 0;          // members assimilated
+    int p = 0;          // index of the last parameter set (A, Gamma, C, Sigma)
+    for (int k = 0; k < d.n_members; ++k) {
+        const int s = k;                      // last state index before this member
+        const double* m = d.f_star_sm + (int64_t)s * T;
+        const double* Sg = d.cov_f_sm + s * tt;
+        const double* A = d.A + p * tt;
+        const double* Gm = d.Gamma + p * tt;
+        const double* C = d.C + p * tt;
+        const double* R = d.Sigma + p * tt;
+        const double* y = d.Y + (int64_t)d.member_beats[k] * T;
+        double* m_new = d.f_star + (int64_t)(s + 1) * T;
+        double* S_new = d.cov_f + (s + 1) * tt;
+        // ---------------- Kalman update (GPI.py:104-150) ----------------
+        la_gemv(v0, A, m, T, 0.0, nullptr);                              // v0 = A m  (x_basis_mean)
+        const bool prior = d.first_is_prior && k == 0;
+        const double* P;
+        if (prior) {
+            P = Sg;                                                      // P_t = cov_prior; f* = 0; R = r_first I
+            for (int i = threadIdx.x; i < T; i += LA_THREADS) v1[i] = y[i];
+            __syncthreads();
+            la_gemm(W2, C, 0, P, 0, T, 1.0, 0.0, nullptr, sm);           // W2 = C P
+            la_gemm(W3, W2, 0, C, 1, T, 1.0, 0.0, nullptr, sm);          // W3 = C P C^T
+            la_add_diag(W3, d.r_first, T);                               //      + R
+        } else {
+            la_gemm(W0, A, 0, Sg, 0, T, 1.0, 0.0, nullptr, sm);          // W0 = A Sigma
+            la_gemm(W1, W0, 0, A, 1, T, 1.0, 1.0, Gm, sm);               // W1 = A Sigma A^T + Gamma = P
+            P = W1;
+            la_gemv(v2, C, v0, T, 0.0, nullptr);                         // f* = C A m
+            for (int i = threadIdx.x; i < T; i += LA_THREADS) v1[i] = y[i] - v2[i];
+            __syncthreads();
+            la_gemm(W2, C, 0, P, 0, T, 1.0, 0.0, nullptr, sm);           // W2 = C P
+            la_gemm(W3, W2, 0, C, 1, T, 1.0, 1.0, R, sm);                // W3 = C P C^T + R = S
+        }
+        // K_t = solve(S^T, C P^T)^T
+        la_transpose(W5, W3, T);                                         // W5 = S^T
+        la_gemm(W4, C, 0, P, 1, T, 1.0, 0.0, nullptr, sm);               // W4 = C P^T
+        la_lu_factor(W5, d.piv, T, sm);
+        la_lu_solve(W5, d.piv, W4, T, sm);                               // W4 = S^-T (C P^T)
+        la_transpose(W6, W4, T);                                         // W6 = K_t
+        la_gemv(m_new, W6, v1, T, 1.0, v0);                              // m+ = A m + K (y - f*)
+        // Joseph form: (I - K C) P (I - K C)^T + K R K^T
+        la_gemm(W2, W6, 0, C, 0, T, -1.0, 0.0, nullptr, sm);             // W2 = -K C
+        la_add_diag(W2, 1.0, T);                                         // W2 = I - K C
+        la_gemm(W0, W2, 0, P, 0, T, 1.0, 0.0, nullptr, sm);              // W0 = IKC P   (P may be W1: W0 is free)
+        la_gemm(W3, W0, 0, W2, 1, T, 1.0, 0.0, nullptr, sm);             // W3 = IKC P IKC^T
+        if (prior) {
+            la_gemm(S_new, W6, 0, W6, 1, T, d.r_first, 1.0, W3, sm);     // + r K K^T
+        } else {
+            la_gemm(W4, W6, 0, R, 0, T, 1.0, 0.0, nullptr, sm);          // W4 = K R
+            la_gemm(S_new, W4, 0, W6, 1, T, 1.0, 1.0, W3, sm);           // S+ = W3 + K R K^T
+        }
+        la_copy(d.f_star_sm + (int64_t)(s + 1) * T, m_new, T);
+        la_copy(d.cov_f_sm + (s + 1) * tt, S_new, n);
+        N += 1;
+        // ---------------- pair smoother (GPI_model.py:705-716, GPI.py:294-299) ----------------
+        if (N > 1) {
+            const double* m0 = d.f_star + (int64_t)s * T;
+            const double* S0 = d.cov_f + s * tt;
+            la_gemm(W0, A, 0, S0, 0, T, 1.0, 0.0, nullptr, sm);          // A S0
+            la_gemm(W1, W0, 0, A, 1, T, 1.0, 1.0, Gm, sm);               // P = A S0 A^T + Gamma
+            la_transpose(W5, W1, T);                                     // P^T
+            la_gemm(W4, A, 0, S0, 1, T, 1.0, 0.0, nullptr, sm);          // A S0^T
+            la_lu_factor(W5, d.piv, T, sm);
+            la_lu_solve(W5, d.piv, W4, T, sm);
+            la_transpose(W6, W4, T);                                     // J
+            la_gemv(v2, A, m0, T, 0.0, nullptr);                         // A m0
+            for (int i = threadIdx.x; i < T; i += LA_THREADS) v2[i] = m_new[i] - v2[i];
+            __syncthreads();
+            la_gemv(d.f_star_sm + (int64_t)s * T, W6, v2, T, 1.0, m0);   // m0 + J (m1 - A m0)
+            la_axpby(W2, 1.0, S_new, -1.0, W1, n);                       // S1 - P
+            la_gemm(W0, W6, 0, W2, 0, T, 1.0, 0.0, nullptr, sm);         // J (S1 - P)
+            la_gemm(d.cov_f_sm + s * tt, W0, 0, W6, 1, T, 1.0, 1.0, S0, sm);   // S0 + J (S1 - P) J^T
+        }
+        // ---------------- MNIW step (GPI_model.py:966-1101) ----------------
+        const bool below = d.estimation_limit <= 0 || N < d.estimation_limit;
+        if (N > 1 && below) {
+            // the reference also factorises P = A cov_ A^T + Gamma here and discards it (:990-998); only a
+            // failure of that factorization is observable (keep previous parameters) -- P is SPD by construction
+            int i1 = mniw_posterior_one(mi, d.f_star_sm + (int64_t)(s + 1) * T, d.f_star_sm + (int64_t)s * T, T, W0, W1, W2, W3, v2, sm);
+            int i2 = mniw_posterior_one(mo, y, d.f_star_sm + (int64_t)(s + 1) * T, T, W0, W1, W2, W3, v2, sm);
+            if ((i1 || i2) && !fail) fail = k + 1;
+        }
+        if (below) {
+            double* An = d.A + (p + 1) * tt; double* Gn = d.Gamma + (p + 1) * tt;
+            double* Cn = d.C + (p + 1) * tt; double* Sn = d.Sigma + (p + 1) * tt;
+            const double gi = *d.int_n0, go = *d.obs_n0;
+            const double fa = d.annealing ? 1.0 / ((double)N * (double)N) : 0.0;
+            for (int i = threadIdx.x; i < n; i += LA_THREADS) {
+                An[i] = d.int_m_mean[i];
+                Cn[i] = d.obs_m_mean[i];
+                const double g = (N > 1) ? d.int_scale[i] * gi / (gi - 2.0) : Gm[i];
+                const double sg = (N > 1) ? d.obs_scale[i] * go / (go - 2.0) : R[i];
+                Gn[i] = g + fa * d.Gamma[i];          // + Gamma[0] / N^2
+                Sn[i] = sg + fa * d.Sigma[i];         // + Sigma[0] / N^2
+            }
+            __syncthreads();
+            p += 1;
+        }
+    }
+    // ---------------- full RTS pass (GPI_model.py:687-703, GPI.py:262-270) ----------------
+    // means = f_star[1:], covars = cov_f[1:], A_prior = A[1:], Gamma_prior = Gamma[1:]
+    const int Tn = d.n_members;
+    const int nA = p;      // len(A[1:])
+    if (Tn >= 1) {
+        // the last state is its own smoothed value
+        la_copy(d.f_star_sm + (int64_t)Tn * T, d.f_star + (int64_t)Tn * T, T);
+        la_copy(d.cov_f_sm + Tn * tt, d.cov_f + Tn * tt, n);
+    }
+    for (int t = Tn - 2; t >= 0; --t) {
+        const int ia = (t < nA ? t : nA - 1) + 1;
+        const double* A = d.A + ia * tt;
+        const double* Gm = d.Gamma + ia * tt;
+        const double* mt = d.f_star + (int64_t)(t + 1) * T;
+        const double* St = d.cov_f + (t + 1) * tt;
+        const double* mn = d.f_star_sm + (int64_t)(t + 2) * T;       // already smoothed successor
+        const double* Sn = d.cov_f_sm + (t + 2) * tt;
+        la_gemm(W0, A, 0, St, 0, T, 1.0, 0.0, nullptr, sm);
+        la_gemm(W1, W0, 0, A, 1, T, 1.0, 1.0, Gm, sm);               // P_t
+        // J = covars[t] A^T inv(P): J^T = inv(P)^T (A covars[t]^T) -> solve P^T X = A St^T
+        la_transpose(W5, W1, T);
+        la_gemm(W4, A, 0, St, 1, T, 1.0, 0.0, nullptr, sm);
+        la_lu_factor(W5, d.piv, T, sm);
+        la_lu_solve(W5, d.piv, W4, T, sm);
+        la_transpose(W6, W4, T);                                     // J_t
+        la_gemv(v2, A, mt, T, 0.0, nullptr);
+        for (int i = threadIdx.x; i < T; i += LA_THREADS) v2[i] = mn[i] - v2[i];
+        __syncthreads();
+        la_gemv(d.f_star_sm + (int64_t)(t + 1) * T, W6, v2, T, 1.0, mt);
+        la_axpby(W2, 1.0, Sn, -1.0, W1, n);
+        la_gemm(W0, W6, 0, W2, 0, T, 1.0, 0.0, nullptr, sm);
+        la_gemm(d.cov_f_sm + (t + 1) * tt, W0, 0, W6, 1, T, 1.0, 1.0, St, sm);
+    }
+    if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
+}
+
+// unit-test hook for the CTA-level routines: op codes below
+__global__ void __launch_bounds__(LA_THREADS)
+la_op_kernel(int op, double* A, double* B, double* C, int* piv, int T, int* info) {
+    __shared__ LaSmem sm;
+    int rc = 0;
+    switch (op) {
+        case 0: la_gemm(C, A, 0, B, 0, T, 1.0, 0.0, nullptr, sm); break;
+        case 1: la_gemm(C, A, 1, B, 0, T, 1.0, 0.0, nullptr, sm); break;
+        case 2: la_gemm(C, A, 0, B, 1, T, 1.0, 0.0, nullptr, sm); break;
+        case 3: la_gemm(C, A, 1, B, 1, T, 2.0, -1.0, C, sm); break;
+        case 4: rc = la_chol(A, T, sm); break;
+        case 5: la_trsm_lower(A, B, T, sm); break;
+        case 6: la_trsm_lower_trans(A, B, T, sm); break;
+        case 7: la_lu_factor(A, piv, T, sm); la_lu_solve(A, piv, B, T, sm); break;
+        case 8: la_symmetrize(A, 0.25, T); break;
+        case 9: la_transpose(C, A, T); break;
+        default: rc = -1;
+    }
+    if (threadIdx.x == 0) info[0] = rc;
+}
+
+}  // namespace
+
+extern "C" int64_t hgp_chain_desc_bytes(void) { return (int64_t)sizeof(hgp_chain_desc); }
+extern "C" int64_t hgp_chain_work_doubles(int T) { return 8 * (int64_t)T * T + 8 * (int64_t)T; }
+
+extern "C" int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream) {
+    HGP_REQUIRE(n_chains >= 0 && T > 0 && T <= 1024, "hgp_chain_run: bad sizes");
+    if (n_chains == 0) return 0;
+    chain_kernel<<<n_chains, LA_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const hgp_chain_desc*>(descs_device), T);
+    HGP_LAUNCH_CHECK("hgp_chain_run");
+    return 0;
+}
+
+extern "C" int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream) {
+    HGP_REQUIRE(T > 0 && T <= 1024, "hgp_la_op: bad T");
+    la_op_kernel<<<1, LA_THREADS, 0, (cudaStream_t)stream>>>(op, A, B, C, piv, T, info);
+    HGP_LAUNCH_CHECK("hgp_la_op");
+    return 0;
+}

@@ -234,3 +234,73 @@ class GPI_model:
             raise LinAlgError(f"linalg.cholesky: Gamma of member {int(bad[0])} is not positive-definite")
         out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals
         return out
+
+    # ---- chain replay -------------------------------------------------------------------------------
+    @classmethod
+    def fresh(cls, x_basis, kernel, ini_sigma, ini_gamma, free_deg=5, estimation_limit=None, annealing=True,
+              device="cuda"):
+        """A fitted, empty dynamic model: GPI_HDP.create_gp_default (GPI_HDP.py:496-535) + GPI_model.GPR_dynamic /
+        initial_conditions (GPI_model.py:115-205) + fit_kernel_params' side effects (:207-241) for the given
+        fitted kernel (const, length, noise) of ConstantKernel*RBF + WhiteKernel."""
+        x = np.asarray(x_basis, dtype=np.float64).reshape(-1)
+        T = x.shape[0]
+        c, ell, noise = (float(v) for v in kernel)
+        d = (x[:, None] / ell - x[None, :] / ell) ** 2
+        K = c * np.exp(-0.5 * d)
+        I = np.eye(T)
+        self = cls(x, [np.zeros(T)], [np.zeros(T)], [I], [ini_sigma * I], [], estimation_limit=estimation_limit,
+                   A=[I], Gamma=[ini_gamma * I], cov_f_sm=[K], device=device)
+        self.cov_f = _stack([K], self.device)
+        self.kernel = (c, ell, noise)
+        self.free_deg = float(free_deg)
+        self.annealing = annealing
+        self.fitted = True
+        return self
+
+    def full_pass_weighted(self, x_trains, y_trains, resp, q=None, q_lat=None, snr=None):
+        """GPI_model.full_pass_weighted (GPI_model.py:377-406) for a fresh fitted dynamic model: assimilate the
+        beats with resp > 0.99 in time order (Kalman + pair smoother + MNIW per member), full RTS pass, then
+        (q, q_lat) over all beats.  One persistent CTA runs the whole chain on the device."""
+        if self.N != 0 or not getattr(self, "fitted", False):
+            raise HgpError("device full_pass_weighted needs a fresh fitted model (GPI_model.fresh); the hyper-fit "
+                           "(GPI.py:610-770) is not built on the device yet")
+        self._check_grid(x_trains)
+        Y = self._beats(y_trains)
+        r = resp if isinstance(resp, torch.Tensor) else torch.from_numpy(np.asarray(resp, dtype=np.float64))
+        active = torch.nonzero(r.to(self.device) > 0.99).flatten()
+        n = int(active.numel())
+        if n == 0:
+            return q, q_lat
+        T, dev = self.T, self.device
+        z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
+        hist = {k: z(n + 1, T, T) for k in ("cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma")}
+        f_star, f_star_sm = z(n + 1, T), z(n + 1, T)
+        f_star[0], f_star_sm[0] = self.f_star[0], self.f_star_sm[0]
+        hist["cov_f"][0], hist["cov_f_sm"][0] = self.cov_f[0], self.cov_f_sm[0]
+        hist["A"][0], hist["Gamma"][0], hist["C"][0], hist["Sigma"][0] = self.A[0], self.Gamma[0], self.C[0], self.Sigma[0]
+        eye = torch.eye(T, dtype=F64, device=dev)
+        c, ell, noise = self.kernel
+        lib = ops._lib.load()
+        desc = dict(n_members=n, first_is_prior=1, annealing=int(self.annealing),
+                    estimation_limit=0 if np.isinf(self.estimation_limit) else int(self.estimation_limit),
+                    r_first=(c + noise) - c, member_beats=active.to(torch.int32).contiguous(), Y=Y,
+                    f_star=f_star, f_star_sm=f_star_sm, **hist,
+                    int_m_mean=self.A[0].clone(), int_m_r_cov=eye.clone(), int_scale=self.Gamma[0].clone(),
+                    int_n0=torch.tensor([self.free_deg], dtype=F64, device=dev),
+                    obs_m_mean=self.C[0].clone(), obs_m_r_cov=eye.clone(), obs_scale=self.Sigma[0].clone(),
+                    obs_n0=torch.tensor([self.free_deg], dtype=F64, device=dev),
+                    work=z(int(lib.hgp_chain_work_doubles(T))), piv=torch.zeros(T, dtype=torch.int32, device=dev),
+                    status=torch.zeros(2, dtype=torch.int32, device=dev))
+        ops.chain_run([desc], T)
+        fail, n_par = (int(v) for v in desc["status"])
+        if fail:
+            raise LinAlgError(f"MNIW factorization failed at member {fail - 1}")
+        self.f_star, self.f_star_sm = f_star, f_star_sm
+        self.cov_f, self.cov_f_sm = hist["cov_f"], hist["cov_f_sm"]
+        self.A, self.Gamma, self.C, self.Sigma = (hist[k][:n_par] for k in ("A", "Gamma", "C", "Sigma"))
+        self.internal = {k[4:]: desc[k] for k in ("int_m_mean", "int_m_r_cov", "int_scale", "int_n0")}
+        self.observation = {k[4:]: desc[k] for k in ("obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0")}
+        self.indexes = [int(i) for i in active.cpu()]
+        self.N = n
+        self._tables = None
+        return self.compute_sq_err_all(x_trains, y_trains), self.compute_q_lat_all(Y)

@@ -203,3 +203,34 @@ def qlat_batched(A, Gamma, P, fmean, A_idx, G_idx, P_idx, fprev_idx, fcur_idx, g
                                ptr(fprev_idx), ptr(fcur_idx), ptr(gamma_scale), J, T, ptr(out), ptr(info),
                                ptr(workspace), workspace.numel(), stream_ptr()), "hgp_qlat_batched")
     return out, info
+
+
+def la_op(op, A, B=None, C=None, T=None):
+    """Unit-test hook: run one CTA-level routine (see hgp_la_op).  Operands are modified in place."""
+    lib = _lib_ready()
+    T = T or A.shape[-1]
+    piv = torch.zeros(T, dtype=I32, device=A.device)
+    info = torch.zeros(1, dtype=I32, device=A.device)
+    check(lib.hgp_la_op(int(op), ptr(A), ptr(B), ptr(C), ptr(piv), T, ptr(info), stream_ptr()), "hgp_la_op")
+    return int(info)
+
+
+def chain_run(descs, T):
+    """descs: list of dicts with the fields of hgp_chain_desc (tensors or scalars).  Runs all chains in one launch."""
+    import ctypes as _ct
+    lib = _lib_ready()
+    n = len(descs)
+    arr = (_lib.ChainDesc * n)()
+    keep = []
+    for i, d in enumerate(descs):
+        for name, _ty in _lib.ChainDesc._fields_:
+            v = d[name]
+            if isinstance(v, torch.Tensor):
+                keep.append(v)
+                v = v.data_ptr()
+            setattr(arr[i], name, v)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    dev = host.cuda()
+    check(lib.hgp_chain_run(ptr(dev), n, T, stream_ptr()), "hgp_chain_run")
+    torch.cuda.current_stream().synchronize()
+    return keep

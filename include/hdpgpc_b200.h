@@ -149,6 +149,35 @@ int hgp_qlat_batched(const double* A, const double* Gamma, const double* P, cons
 int hgp_gemm_batched(const double* A, const int* ia, const double* B, const int* ib, double* C, int64_t J, int T,
                      int lowerA, int transA, void* stream);
 
+/* ---- cluster propagation (chain replay): GPI_model.full_pass_weighted (GPI_model.py:377-406) =
+ *      per member Kalman update (IterativeGaussianProcess.posterior, GPI.py:72-151) + pair smoother
+ *      (backward_notrange, GPI.py:272-300) + MNIW step (bayesian_new_params, GPI_model.py:966-1101;
+ *      matrix_normal_inv_wishart.posterior :1300-1344), then the full RTS pass (backward, GPI.py:240-270).
+ * One persistent CTA per (cluster, lead) chain; shared basis grid (x_train == x_basis), dynamic model.
+ * Histories are pre-allocated by the caller with capacity n_members + 1; entry 0 of each is the chain's
+ * initial state (GPI_model.initial_conditions, GPI_model.py:115-175).  All pointers are device pointers. */
+typedef struct hgp_chain_desc {
+    int n_members;            /* members to assimilate, ascending beat order */
+    int first_is_prior;       /* 1: the first member sees the GP prior: P = cov, f* = 0, R = r_first I (GPI.py:136-139) */
+    int annealing;            /* Gamma' += Gamma[0]/N^2, Sigma' += Sigma[0]/N^2 (GPI_model.py:1083-1091) */
+    int estimation_limit;     /* <= 0: none */
+    double r_first;           /* (c + noise) - c of the fitted kernel (kernel(x) - kernel(x, x), GPI.py:139) */
+    const int* member_beats;  /* [n_members] row of Y per member */
+    const double* Y;          /* beats plane [N][T] */
+    double *f_star, *f_star_sm;                 /* [n_members + 1][T] */
+    double *cov_f, *cov_f_sm, *A, *Gamma, *C, *Sigma;   /* [n_members + 1][T][T] */
+    double *int_m_mean, *int_m_r_cov, *int_scale, *int_n0;   /* MNIW over (A, Gamma): in/out; n0 is a device scalar */
+    double *obs_m_mean, *obs_m_r_cov, *obs_scale, *obs_n0;   /* MNIW over (C, Sigma) */
+    double* work;             /* >= hgp_chain_work_doubles(T) */
+    int* piv;                 /* >= T */
+    int* status;              /* [2] out: first member (1-based) whose MNIW factorization failed or 0; parameter sets written */
+} hgp_chain_desc;
+int64_t hgp_chain_desc_bytes(void);
+int64_t hgp_chain_work_doubles(int T);
+int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream);
+/* Unit-test hook for the CTA-level routines the chain kernel is built from (gemm variants, chol, trsm, LU solve). */
+int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,67 @@ def test_gemm_and_qlat_vs_oracle(T):
         assert abs(float(out[j]) - refv) < TOL * abs(refv)
 
 
+@pytest.mark.parametrize("T", [7, 30, 90, 130])
+def test_cta_linear_algebra(T):
+    """The CTA-level routines the chain kernel is built from, against numpy."""
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(T)
+    A = rng.standard_normal((T, T)); B = rng.standard_normal((T, T)); C0 = rng.standard_normal((T, T))
+    for op, ref in ((0, A @ B), (1, A.T @ B), (2, A @ B.T)):
+        C = cu(np.zeros((T, T)))
+        assert ops.la_op(op, cu(A), cu(B), C) == 0
+        assert np.max(np.abs(C.cpu().numpy() - ref)) < 1e-12 * np.max(np.abs(ref))
+    C = cu(C0)
+    ops.la_op(3, cu(A), cu(B), C)
+    ref = 2.0 * A.T @ B.T - C0
+    assert np.max(np.abs(C.cpu().numpy() - ref)) < 1e-12 * np.max(np.abs(ref))
+    S = random_spd(rng, 1, T, cond=1e4)[0]
+    Ld = cu(S)
+    assert ops.la_op(4, Ld) == 0
+    Lr = np.linalg.cholesky(S)
+    assert np.max(np.abs(Ld.cpu().numpy() - Lr)) < 1e-11 * np.max(np.abs(Lr))
+    X = cu(B); ops.la_op(5, cu(Lr), X)
+    assert np.max(np.abs(Lr @ X.cpu().numpy() - B)) < 1e-9 * np.max(np.abs(B))
+    X = cu(B); ops.la_op(6, cu(Lr), X)
+    assert np.max(np.abs(Lr.T @ X.cpu().numpy() - B)) < 1e-9 * np.max(np.abs(B))
+    G = A + 0.1 * T * np.eye(T) * rng.choice([-1, 1], size=T)      # general, pivoting matters
+    X = cu(B); ops.la_op(7, cu(G), X)
+    assert np.max(np.abs(G @ X.cpu().numpy() - B)) < 1e-9 * np.max(np.abs(B))
+    bad = cu(np.diag(np.r_[np.ones(T - 1), -1.0]))
+    assert ops.la_op(4, bad) == T
+
+
+@pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2", "offline_rec100_T90_L1"])
+def test_chain_replay_vs_reference(golden, name):
+    """full_pass_weighted on the device (Kalman + pair smoother + MNIW per member, full RTS pass) against the
+    reference's golden chain dumps: per-step states and the (q, q_lat) it returns."""
+    import hdpgpc_b200 as hb
+    z = golden(name)
+    Y = z["data"]
+    full = "chain_0_Sigma" in z.files
+    for m in range(int(z["n_chain"])):
+        pre = f"chain_{m}_"
+        gp = hb.GPI_model.fresh(z["x_basis"], z[pre + "kernel"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]),
+                                free_deg=float(z["free_deg_MNIV"]))
+        q, ql = gp.full_pass_weighted(None, Y[:, :, [0]], z[pre + "resp"])
+        assert gp.indexes == [int(i) for i in z[pre + "indexes"]]
+        assert rel(q, z[pre + "q"]) < TOL
+        assert rel(ql, z[pre + "q_lat"]) < TOL
+        scale = np.max(np.abs(z[pre + "f_star"]))
+        assert np.max(np.abs(gp.f_star.cpu().numpy() - z[pre + "f_star"][:, :, 0])) < 1e-8 * scale
+        assert np.max(np.abs(gp.f_star_sm.cpu().numpy() - z[pre + "f_star_sm"][:, :, 0])) < 1e-8 * scale
+        for nm in ["cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma"]:
+            mine = getattr(gp, nm).cpu().numpy()
+            if full:
+                ref = z[pre + nm]
+                assert mine.shape == ref.shape
+                assert np.max(np.abs(mine - ref)) < 1e-8 * np.max(np.abs(ref))
+            else:
+                assert mine.shape[0] == int(z[pre + nm + "_len"])
+                ref = z[pre + nm + "_last"]
+                assert np.max(np.abs(mine[-1] - ref)) < 1e-8 * np.max(np.abs(ref))
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
