@@ -8,7 +8,7 @@ behind the C ABI in include/hdpgpc_b200.h; there is no CPU fallback.
 """
 from ._lib import HgpError, load as load_library  # noqa: F401
 from .build import build  # noqa: F401
-from .model import GPI_model, LinAlgError  # noqa: F401
+from .model import GPI_model, LinAlgError, full_pass_weighted_batch  # noqa: F401
 from .hdp import GPI_HDP, EStepEngine, LeadTables  # noqa: F401
 
 __version__ = "0.1.0"

@@ -25,7 +25,7 @@ struct Mniw {
 
 // matrix_normal_inv_wishart.posterior for n_k = 1 with zero covariance terms and sse_matrix = I
 // (GPI_model.py:1300-1344).  W0..W3: T x T scratch.  Returns chol info (0 = ok).
-__device__ int mniw_posterior_one(Mniw d, const double* y1, const double* y2, int T, double* W0, double* W1, double* W2,
+__device__ __noinline__ int mniw_posterior_one(Mniw d, const double* y1, const double* y2, int T, double* W0, double* W1, double* W2,
                                   double* W3, double* vec, LaSmem& sm) {
     const int n = T * T;
     const double n0 = *d.n0;

@@ -55,9 +55,24 @@ def snr_state_index(indexes, n_states, n_samps):
     return np.minimum(np.maximum(j, 1), n_states - 1)
 
 
+class _Appended:
+    """history + one extra element, indexable like the list the reference builds with .copy() + .append()."""
+
+    def __init__(self, hist, extra):
+        self.hist, self.extra = hist, extra
+
+    def __len__(self):
+        return self.hist.shape[0] + 1
+
+    def __getitem__(self, i):
+        n = len(self)
+        i = i + n if i < 0 else i
+        return self.extra if i == n - 1 else self.hist[i]
+
+
 class GPI_model:
     def __init__(self, x_basis, f_star, f_star_sm, C, Sigma, indexes, estimation_limit=None,
-                 A=None, Gamma=None, cov_f_sm=None, device="cuda"):
+                 A=None, Gamma=None, cov_f_sm=None, cov_f=None, kernel=None, device="cuda"):
         self.device = torch.device(device)
         self.x_basis = np.asarray(x_basis, dtype=np.float64).reshape(-1)
         self.T = self.x_basis.shape[0]
@@ -68,6 +83,8 @@ class GPI_model:
         self.A = None if A is None else _stack(A, self.device)
         self.Gamma = None if Gamma is None else _stack(Gamma, self.device)
         self.cov_f_sm = None if cov_f_sm is None else _stack(cov_f_sm, self.device)
+        self.cov_f = None if cov_f is None else _stack(cov_f, self.device)
+        self.kernel = None if kernel is None else tuple(float(v) for v in kernel)   # (const, length, noise)
         self.indexes = [int(i) for i in indexes]
         self.N = len(self.indexes)
         self.estimation_limit = np.inf if estimation_limit is None else estimation_limit
@@ -79,7 +96,7 @@ class GPI_model:
         """gp: a reference GPI_model (or any object with the same list attributes)."""
         return cls(gp.x_basis, gp.f_star, gp.f_star_sm, gp.C, gp.Sigma, gp.indexes,
                    estimation_limit=getattr(gp, "estimation_limit", None), A=gp.A, Gamma=gp.Gamma,
-                   cov_f_sm=gp.cov_f_sm, device=device)
+                   cov_f_sm=gp.cov_f_sm, cov_f=gp.cov_f, kernel=getattr(gp, "kernel", None), device=device)
 
     @classmethod
     def from_dump(cls, z, prefix, device="cuda"):
@@ -87,7 +104,7 @@ class GPI_model:
         g = lambda k: z[prefix + k]
         return cls(g("x_basis"), g("f_star"), g("f_star_sm"), g("C"), g("Sigma"), g("indexes"),
                    estimation_limit=float(g("estimation_limit")), A=g("A"), Gamma=g("Gamma"),
-                   cov_f_sm=g("cov_f_sm"), device=device)
+                   cov_f_sm=g("cov_f_sm"), cov_f=g("cov_f"), kernel=g("kernel"), device=device)
 
     # ---- index rules (host integer work) ----
     def find_closest_lower(self, t):
@@ -178,9 +195,27 @@ class GPI_model:
 
     def log_sq_error(self, x_train, y, mean=None, cov=None, C=None, Sigma=None, i=None, proj=False, first=False):
         """GPI_model.log_sq_error (GPI_model.py:250-286) for params=None; i=None / -1 = last state."""
-        if mean is not None or proj:
-            raise HgpError("log_sq_error with explicit (mean, cov, C, Sigma) / proj is not built yet")
+        if proj:
+            raise HgpError("log_sq_error(proj=True) is not built")
         self._check_grid(x_train)
+        if mean is not None:
+            # explicit parameters (estimate_new path, :261-264 -> observe :657-660): mean' = C @ mean, cov = Sigma
+            dev = self.device
+            Yb = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
+                                                        dtype=np.float64).reshape(1, -1)))
+            Cm = _stack(C, dev).reshape(1, self.T, self.T)
+            mv = _vecs(mean, dev).reshape(1, self.T)
+            zero = torch.zeros(1, dtype=torch.int32, device=dev)
+            mu = ops.emission_means(Cm, mv, zero, zero)
+            add = None
+            if first:
+                add = (1e-2 * torch.mean(torch.diagonal(self.Sigma[0]))).reshape(1)
+            Lf, info = ops.chol_batched(_stack(Sigma, dev).reshape(1, self.T, self.T), add_diag=add)
+            if int(info[0]):
+                raise LinAlgError("linalg.cholesky: explicit Sigma is not positive-definite")
+            W = ops.tri_inverse_batched(Lf)
+            q = ops.score_pairs(Yb, mu, W, torch.zeros((1, 1), dtype=torch.int32, device=dev), zero)
+            return q[0, 0]
         Y = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
                                                    dtype=np.float64).reshape(1, -1)))
         tb = self.tables()
@@ -235,6 +270,56 @@ class GPI_model:
         out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals
         return out
 
+    # ---- online extras ------------------------------------------------------------------------------
+    def posterior_weighted(self, x_train, y, h, t=None):
+        """GPI_model.posterior_weighted (GPI_model.py:561-582), t=None: one Kalman update
+        (IterativeGaussianProcess.posterior, GPI.py:72-151) from the last filtered state with Gamma/h, Sigma/h.
+        Nothing is stored.  Returns (f (T,), cov (T,T))."""
+        if t is not None:
+            raise HgpError("posterior_weighted(t=...) is not built")
+        self._check_grid(x_train)
+        if not h > 0.0:
+            return self.f_star[-1].clone(), self.cov_f[-1].clone()
+        T, dev = self.T, self.device
+        Y = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
+                                                   dtype=np.float64).reshape(1, -1)))
+        z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
+        hist = {k: z(2, T, T) for k in ("cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma")}
+        f_star, f_star_sm = z(2, T), z(2, T)
+        f_star[0] = f_star_sm[0] = self.f_star[-1]
+        hist["cov_f"][0] = hist["cov_f_sm"][0] = self.cov_f[-1]
+        hist["A"][0], hist["C"][0] = self.A[-1], self.C[-1]
+        hist["Gamma"][0], hist["Sigma"][0] = self.Gamma[-1] / h, self.Sigma[-1] / h
+        prior = self.N == 0 and self.kernel is not None
+        r_first = 0.0
+        if prior:
+            c, ell, noise = self.kernel
+            r_first = ((c + noise) - c) / h
+        lib = ops._lib.load()
+        scratch = lambda: z(T, T)
+        desc = dict(n_members=1, first_is_prior=int(prior), annealing=0, estimation_limit=0, r_first=r_first,
+                    member_beats=torch.zeros(1, dtype=torch.int32, device=dev), Y=Y, f_star=f_star, f_star_sm=f_star_sm,
+                    **hist, int_m_mean=scratch(), int_m_r_cov=scratch(), int_scale=scratch(),
+                    int_n0=torch.tensor([5.0], dtype=F64, device=dev), obs_m_mean=scratch(), obs_m_r_cov=scratch(),
+                    obs_scale=scratch(), obs_n0=torch.tensor([5.0], dtype=F64, device=dev),
+                    work=z(int(lib.hgp_chain_work_doubles(T))), piv=torch.zeros(T, dtype=torch.int32, device=dev),
+                    status=torch.zeros(2, dtype=torch.int32, device=dev))
+        ops.chain_run([desc], T)
+        return f_star[1], hist["cov_f"][1]
+
+    def smoother_weighted(self, x_train, y, h):
+        """GPI_model.smoother_weighted (:726-738): histories with the would-be posterior appended.  Returns views
+        that support [-1] / len() like the reference's lists without copying the histories."""
+        f, cov = self.posterior_weighted(x_train, y, h)
+        return (_Appended(self.f_star, f), _Appended(self.cov_f, cov), _Appended(self.C, self.C[-1]),
+                _Appended(self.Sigma, self.Sigma[-1]))
+
+    def estimate_new(self, x_train, y, h=1.0):
+        """GPI_HDP.estimate_new (GPI_HDP.py:2830-2842): score of y as if it had already been absorbed."""
+        mean_, cov_, C_, Sigma_ = self.smoother_weighted(x_train, y, h)
+        return self.log_sq_error(x_train, y, mean=mean_[-1], cov=cov_[-1], C=C_[-1], Sigma=Sigma_[-1], i=-1,
+                                 first=(len(self.indexes) == 1))
+
     # ---- chain replay -------------------------------------------------------------------------------
     @classmethod
     def fresh(cls, x_basis, kernel, ini_sigma, ini_gamma, free_deg=5, estimation_limit=None, annealing=True,
@@ -252,25 +337,22 @@ class GPI_model:
                    A=[I], Gamma=[ini_gamma * I], cov_f_sm=[K], device=device)
         self.cov_f = _stack([K], self.device)
         self.kernel = (c, ell, noise)
+        self.ini_cov_is_prior = True
         self.free_deg = float(free_deg)
         self.annealing = annealing
         self.fitted = True
         return self
 
-    def full_pass_weighted(self, x_trains, y_trains, resp, q=None, q_lat=None, snr=None):
-        """GPI_model.full_pass_weighted (GPI_model.py:377-406) for a fresh fitted dynamic model: assimilate the
-        beats with resp > 0.99 in time order (Kalman + pair smoother + MNIW per member), full RTS pass, then
-        (q, q_lat) over all beats.  One persistent CTA runs the whole chain on the device."""
+    def _chain_prepare(self, Y, resp):
+        """Allocate the histories of a fresh chain and fill its hgp_chain_desc (None if no member)."""
         if self.N != 0 or not getattr(self, "fitted", False):
             raise HgpError("device full_pass_weighted needs a fresh fitted model (GPI_model.fresh); the hyper-fit "
                            "(GPI.py:610-770) is not built on the device yet")
-        self._check_grid(x_trains)
-        Y = self._beats(y_trains)
         r = resp if isinstance(resp, torch.Tensor) else torch.from_numpy(np.asarray(resp, dtype=np.float64))
         active = torch.nonzero(r.to(self.device) > 0.99).flatten()
         n = int(active.numel())
         if n == 0:
-            return q, q_lat
+            return None
         T, dev = self.T, self.device
         z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
         hist = {k: z(n + 1, T, T) for k in ("cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma")}
@@ -281,7 +363,7 @@ class GPI_model:
         eye = torch.eye(T, dtype=F64, device=dev)
         c, ell, noise = self.kernel
         lib = ops._lib.load()
-        desc = dict(n_members=n, first_is_prior=1, annealing=int(self.annealing),
+        return dict(n_members=n, first_is_prior=1, annealing=int(self.annealing),
                     estimation_limit=0 if np.isinf(self.estimation_limit) else int(self.estimation_limit),
                     r_first=(c + noise) - c, member_beats=active.to(torch.int32).contiguous(), Y=Y,
                     f_star=f_star, f_star_sm=f_star_sm, **hist,
@@ -291,16 +373,55 @@ class GPI_model:
                     obs_n0=torch.tensor([self.free_deg], dtype=F64, device=dev),
                     work=z(int(lib.hgp_chain_work_doubles(T))), piv=torch.zeros(T, dtype=torch.int32, device=dev),
                     status=torch.zeros(2, dtype=torch.int32, device=dev))
-        ops.chain_run([desc], T)
+
+    def _chain_finish(self, desc):
         fail, n_par = (int(v) for v in desc["status"])
         if fail:
             raise LinAlgError(f"MNIW factorization failed at member {fail - 1}")
-        self.f_star, self.f_star_sm = f_star, f_star_sm
-        self.cov_f, self.cov_f_sm = hist["cov_f"], hist["cov_f_sm"]
-        self.A, self.Gamma, self.C, self.Sigma = (hist[k][:n_par] for k in ("A", "Gamma", "C", "Sigma"))
+        self.f_star, self.f_star_sm = desc["f_star"], desc["f_star_sm"]
+        self.cov_f, self.cov_f_sm = desc["cov_f"], desc["cov_f_sm"]
+        self.A, self.Gamma, self.C, self.Sigma = (desc[k][:n_par] for k in ("A", "Gamma", "C", "Sigma"))
         self.internal = {k[4:]: desc[k] for k in ("int_m_mean", "int_m_r_cov", "int_scale", "int_n0")}
         self.observation = {k[4:]: desc[k] for k in ("obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0")}
-        self.indexes = [int(i) for i in active.cpu()]
-        self.N = n
+        self.indexes = [int(i) for i in desc["member_beats"].cpu()]
+        self.N = desc["n_members"]
         self._tables = None
+
+    def full_pass_weighted(self, x_trains, y_trains, resp, q=None, q_lat=None, snr=None):
+        """GPI_model.full_pass_weighted (GPI_model.py:377-406) for a fresh fitted dynamic model: assimilate the
+        beats with resp > 0.99 in time order (Kalman + pair smoother + MNIW per member), full RTS pass, then
+        (q, q_lat) over all beats.  One persistent CTA runs the whole chain on the device."""
+        self._check_grid(x_trains)
+        Y = self._beats(y_trains)
+        desc = self._chain_prepare(Y, resp)
+        if desc is None:
+            return q, q_lat
+        ops.chain_run([desc], self.T)
+        self._chain_finish(desc)
         return self.compute_sq_err_all(x_trains, y_trains), self.compute_q_lat_all(Y)
+
+
+def full_pass_weighted_batch(models, Y_planes, resp):
+    """All (cluster, lead) chains of one sweep in ONE launch (one CTA per chain): models[ld][m] fresh fitted
+    GPI_model objects, Y_planes [L, N, T], resp [N, M] one-hot.  The reference runs them one after the other
+    (estimate_q_all, GPI_HDP.py:2879-2907).  Returns (q [N, M, L], q_lat [N, M, L])."""
+    L, N, T = Y_planes.shape
+    M = len(models[0])
+    descs, owners = [], []
+    for ld in range(L):
+        for m in range(M):
+            d = models[ld][m]._chain_prepare(Y_planes[ld], resp[:, m])
+            if d is not None:
+                descs.append(d)
+                owners.append((ld, m))
+    if descs:
+        ops.chain_run(descs, T)
+    dev = Y_planes.device
+    q = torch.zeros((N, M, L), dtype=F64, device=dev)
+    q_lat = torch.zeros((N, M, L), dtype=F64, device=dev)
+    for d, (ld, m) in zip(descs, owners):
+        gp = models[ld][m]
+        gp._chain_finish(d)
+        q[:, m, ld] = gp.compute_sq_err_all(None, Y_planes[ld])
+        q_lat[:, m, ld] = gp.compute_q_lat_all(Y_planes[ld])
+    return q, q_lat

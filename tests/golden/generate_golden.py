@@ -337,6 +337,39 @@ def inducing():
     print(f"inducing_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def online_extras():
+    """Online scoring of a beat "as if already absorbed": GPI_HDP.estimate_new (GPI_HDP.py:2830-2842) ->
+    GPI_model.smoother_weighted (GPI_model.py:726-738) -> posterior_weighted (:561-582) -> log_sq_error with
+    explicit (mean, cov, C, Sigma)."""
+    data, _ = load_record("100", 30, [0], 3)
+    N, T, L = data.shape
+    sw, x_trains, x_basis, hyper = make_model(data)
+    out = dict(data=data, x_basis=x_basis)
+    xt = torch.from_numpy(x_trains)
+    yt = torch.from_numpy(data)
+    xb = torch.from_numpy(x_basis)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for tag, members in (("many", [0, 2, 3, 5, 8, 9, 13, 14, 20]), ("one", [4])):
+            gp = sw.create_gp_default()
+            resp = torch.zeros(N)
+            resp[members] = 1.0
+            gp.full_pass_weighted(xt, yt[:, :, [0]], resp)
+            dump_gp(gp, f"{tag}_", out, full=True)
+            qs, means, covs = [], [], []
+            for n in range(22, 30):
+                qs.append(float(sw.estimate_new(n, gp, xb, yt[n, :, [0]], h=1.0)))
+                f, c = gp.posterior_weighted(xb, yt[n, :, [0]], 1.0)
+                means.append(npy(f)); covs.append(npy(c))
+            out[f"{tag}_estimate_new"] = np.array(qs)
+            out[f"{tag}_post_mean"] = np.stack(means)
+            out[f"{tag}_post_cov"] = np.stack(covs)
+            f, c = gp.posterior_weighted(xb, yt[25, :, [0]], 0.5)
+            out[f"{tag}_post_mean_h05"] = npy(f); out[f"{tag}_post_cov_h05"] = npy(c)
+    path = os.path.join(HERE, "online_T30.npz")
+    np.savez_compressed(path, **out)
+    print(f"online_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 SCENARIOS = {
     # full state dumps at T=30 (every 3rd sample of the bundled T=90 beats keeps fixtures small)
     "offline_rec100_T30_L1": lambda: offline_scenario("offline_rec100_T30_L1", "100", 40, [0], 3, 24, True),
@@ -345,6 +378,7 @@ SCENARIOS = {
     "offline_rec100_T90_L1": lambda: offline_scenario("offline_rec100_T90_L1", "100", 40, [0], 1, 24, False),
     "hmm_synth": hmm_synth,
     "inducing_T30": inducing,
+    "online_T30": online_extras,
 }
 
 if __name__ == "__main__":

@@ -208,6 +208,25 @@ def test_chain_replay_vs_reference(golden, name):
                 assert np.max(np.abs(mine[-1] - ref)) < 1e-8 * np.max(np.abs(ref))
 
 
+def test_online_extras_vs_reference(golden):
+    """estimate_new -> smoother_weighted -> posterior_weighted -> log_sq_error(mean, cov, C, Sigma) on the device."""
+    import hdpgpc_b200 as hb
+    z = golden("online_T30")
+    Y = z["data"][:, :, 0]
+    for tag in ("many", "one"):
+        gp = hb.GPI_model.from_dump(z, tag + "_")
+        for k, n in enumerate(range(22, 30)):
+            f, cov = gp.posterior_weighted(None, Y[n], 1.0)
+            assert rel(f, z[tag + "_post_mean"][k][:, 0]) < 1e-7 or np.max(np.abs(f.cpu().numpy() - z[tag + "_post_mean"][k][:, 0])) < 1e-8 * np.max(np.abs(z[tag + "_post_mean"][k]))
+            assert np.max(np.abs(cov.cpu().numpy() - z[tag + "_post_cov"][k])) < 1e-8 * np.max(np.abs(z[tag + "_post_cov"][k]))
+            q = float(gp.estimate_new(None, Y[n]))
+            assert abs(q - z[tag + "_estimate_new"][k]) < TOL * abs(z[tag + "_estimate_new"][k])
+        f, cov = gp.posterior_weighted(None, Y[25], 0.5)
+        assert np.max(np.abs(cov.cpu().numpy() - z[tag + "_post_cov_h05"])) < 1e-8 * np.max(np.abs(z[tag + "_post_cov_h05"]))
+        means, covs, Cs, Sigs = gp.smoother_weighted(None, Y[25], 1.0)
+        assert len(means) == gp.f_star.shape[0] + 1 and means[-1].shape == (Y.shape[1],)
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")

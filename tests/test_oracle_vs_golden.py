@@ -142,3 +142,19 @@ def test_table_form_matches_object_form(golden):
         s_of = np.where(first, nF, i_vals).reshape(N, 1)
         q = O.score_states(Y, mu, Sig, s_of, np.arange(nF + 1), add)[:, 0]
         assert rel(q, z["q_all"][:, m, 0]) < 1e-12
+
+
+def test_online_extras(golden):
+    """estimate_new / posterior_weighted."""
+    z = golden("online_T30")
+    Y = z["data"][:, :, 0]
+    for tag in ("many", "one"):
+        gp = O.OracleGP.from_dump(z, tag + "_")
+        for k, n in enumerate(range(22, 30)):
+            m, P = gp.posterior_weighted(None, Y[n], 1.0)
+            assert np.max(np.abs(m - z[tag + "_post_mean"][k][:, 0])) < 1e-9 * np.max(np.abs(m))
+            assert np.max(np.abs(P - z[tag + "_post_cov"][k])) < 1e-9 * np.max(np.abs(P))
+            assert abs(gp.estimate_new(None, Y[n]) - z[tag + "_estimate_new"][k]) < 1e-9 * abs(z[tag + "_estimate_new"][k])
+        m, P = gp.posterior_weighted(None, Y[25], 0.5)
+        assert np.max(np.abs(m - z[tag + "_post_mean_h05"][:, 0])) < 1e-9 * np.max(np.abs(m))
+        assert np.max(np.abs(P - z[tag + "_post_cov_h05"])) < 1e-9 * np.max(np.abs(P))
