@@ -37,6 +37,8 @@ PROTOTYPES = {
     "hgp_chain_work_doubles": (_i64, [_int]),
     "hgp_chain_run": (_int, [_p, _int, _int, _p]),
     "hgp_la_op": (_int, [_int, _p, _p, _p, _p, _int, _p, _p]),
+    "hgp_pred_dist_work_doubles": (_i64, [_i64, _int, _int]),
+    "hgp_pred_dist_inducing": (_int, [_p, _int, _p, _i64, _int, _p, _p, _p, _p, _i64, _dbl, _dbl, _dbl, _p, _p, _p, _p, _p]),
     "hgp_emission_means": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
 }
 

@@ -258,3 +258,122 @@ extern "C" int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int 
     HGP_LAUNCH_CHECK("hgp_la_op");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Emission distribution on a grid that differs from the basis grid: IterativeGaussianProcess.pred_dist
+// (reference GPI.py:457-503, kernel branch :470-501) -- kernel-matrix construction, Cholesky, two triangular
+// solves and the projected covariance, one CTA per (state, grid) item.  All matrices are embedded in D x D
+// workspaces, D = max(n_b, n_x) (identity padding on the Cholesky diagonal, zeros elsewhere), so the square
+// CTA-level routines apply unchanged.
+//   K_bb = c exp(-(xb_i - xb_j)^2 / (2 l^2)),  K_bx likewise,  K_xx = the same + noise on the diagonal
+//   L = chol(sym(K_bb) + 1e-4 max(mean|diag Sigma|, eps) I);  W = K_bb^{-1} K_bx;  f* = W^T mu
+//   cov = mean(diag Sigma) I                      if all(isclose(diag Sigma, mean diag Sigma))   (:497-498)
+//       = sym(K_xx - K_bx^T W + W^T Sigma W) + 1e-6 I   otherwise                                (:500-501)
+namespace {
+
+__global__ void __launch_bounds__(LA_THREADS)
+pred_dist_kernel(const double* __restrict__ x_basis, int nb, const double* __restrict__ x_post, int64_t x_post_stride,
+                 int nx, const double* __restrict__ mu, const int* __restrict__ mu_idx,
+                 const double* __restrict__ Sigma, const int* __restrict__ sig_idx, double kc, double kl, double knoise,
+                 double* __restrict__ fout, double* __restrict__ covout, double* __restrict__ work, int* __restrict__ info) {
+    __shared__ LaSmem sm;
+    __shared__ int s_const;
+    const int64_t it = blockIdx.x;
+    const int D = max(nb, nx);
+    const int64_t dd = (int64_t)D * D;
+    double* Kbb = work + it * 5 * dd;     // -> chol factor
+    double* Kbx = Kbb + dd;               // -> W
+    double* Sg = Kbx + dd;                // Sigma padded
+    double* T1 = Sg + dd;
+    double* T2 = T1 + dd;
+    const double* xp = x_post + it * x_post_stride;
+    const double* S = Sigma + (int64_t)sig_idx[it] * nb * nb;
+    const double* m = mu + (int64_t)mu_idx[it] * nb;
+    const int tid = threadIdx.x;
+    // mean of diag Sigma, constant-diagonal test
+    double part = 0.0, parta = 0.0;
+    for (int i = tid; i < nb; i += LA_THREADS) { part += S[(int64_t)i * nb + i]; parta += fabs(S[(int64_t)i * nb + i]); }
+    part = warp_sum(part); parta = warp_sum(parta);
+    if ((tid & 31) == 0) { sm.red[tid >> 5] = part; sm.red[8 + (tid >> 5)] = parta; }
+    if (tid == 0) s_const = 1;
+    __syncthreads();
+    double dmean = 0.0, dmeana = 0.0;
+    for (int w = 0; w < LA_THREADS / 32; ++w) { dmean += sm.red[w]; dmeana += sm.red[8 + w]; }
+    dmean /= nb; dmeana /= nb;
+    __syncthreads();
+    for (int i = tid; i < nb; i += LA_THREADS) {
+        const double d = S[(int64_t)i * nb + i];
+        if (!(fabs(d - dmean) <= 1e-8 + 1e-5 * fabs(dmean))) s_const = 0;      // torch.isclose defaults
+    }
+    // kernel matrices (embedded)
+    for (int idx = tid; idx < D * D; idx += LA_THREADS) {
+        const int r = idx / D, c = idx % D;
+        double kbb = (r == c) ? 1.0 : 0.0, kbx = 0.0, sg = 0.0;
+        if (r < nb && c < nb) {
+            const double d = x_basis[r] / kl - x_basis[c] / kl;
+            kbb = kc * exp(-0.5 * d * d);
+            sg = S[(int64_t)r * nb + c];
+        }
+        if (r < nb && c < nx) {
+            const double d = x_basis[r] / kl - xp[c] / kl;
+            kbx = kc * exp(-0.5 * d * d);
+        }
+        Kbb[idx] = kbb; Kbx[idx] = kbx; Sg[idx] = sg;
+    }
+    __syncthreads();
+    const int is_const = s_const;
+    const double jitter = 1e-4 * fmax(dmeana, HGP_EPS);
+    for (int i = tid; i < nb; i += LA_THREADS) Kbb[(int64_t)i * D + i] += jitter;   // K_bb is exactly symmetric already
+    __syncthreads();
+    int rc = la_chol(Kbb, D, sm);
+    la_copy(T1, Kbx, (int)dd);                       // keep K_bx
+    la_trsm_lower(Kbb, Kbx, D, sm);
+    la_trsm_lower_trans(Kbb, Kbx, D, sm);            // Kbx = W
+    // f* = W^T mu
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int c = warp; c < nx; c += LA_THREADS / 32) {
+            double acc = 0.0;
+            for (int r = lane; r < nb; r += 32) acc += Kbx[(int64_t)r * D + c] * m[r];
+            acc = warp_sum(acc);
+            if (lane == 0) fout[it * nx + c] = acc;
+        }
+    }
+    double* cov = covout + it * (int64_t)nx * nx;
+    if (is_const) {
+        for (int idx = tid; idx < nx * nx; idx += LA_THREADS) cov[idx] = (idx / nx == idx % nx) ? dmean : 0.0;
+    } else {
+        la_gemm(T2, Sg, 0, Kbx, 0, D, 1.0, 0.0, nullptr, sm);          // Sigma W
+        la_gemm(Sg, Kbx, 1, T2, 0, D, 1.0, 0.0, nullptr, sm);          // W^T Sigma W      (Sg reused)
+        la_gemm(T2, T1, 1, Kbx, 0, D, -1.0, 1.0, Sg, sm);              // - K_bx^T W + W^T Sigma W
+        for (int idx = tid; idx < nx * nx; idx += LA_THREADS) {
+            const int r = idx / nx, c = idx % nx;
+            const double d = xp[r] / kl - xp[c] / kl;
+            double kxx = (r == c) ? kc + knoise : kc * exp(-0.5 * d * d);   // kernel(x): RBF diagonal is exactly 1, + white noise
+            const double a = kxx + T2[(int64_t)r * D + c];
+            const double b = ((r == c) ? kc + knoise : kc * exp(-0.5 * d * d)) + T2[(int64_t)c * D + r];
+            cov[idx] = 0.5 * (a + b) + ((r == c) ? 1e-6 : 0.0);
+        }
+    }
+    if (tid == 0) info[it] = rc;
+}
+
+}  // namespace
+
+extern "C" int64_t hgp_pred_dist_work_doubles(int64_t n_items, int nb, int nx) {
+    const int64_t D = nb > nx ? nb : nx;
+    return n_items * 5 * D * D;
+}
+
+extern "C" int hgp_pred_dist_inducing(const double* x_basis, int nb, const double* x_post, int64_t x_post_stride, int nx,
+                                      const double* mu, const int* mu_idx, const double* Sigma, const int* sig_idx,
+                                      int64_t n_items, double kernel_const, double kernel_length, double kernel_noise,
+                                      double* f_out, double* cov_out, double* work, int* info, void* stream) {
+    HGP_REQUIRE(n_items >= 0 && nb > 0 && nx > 0 && nb <= 1024 && nx <= 1024, "hgp_pred_dist_inducing: bad sizes");
+    if (n_items == 0) return 0;
+    pred_dist_kernel<<<(unsigned)n_items, LA_THREADS, 0, (cudaStream_t)stream>>>(
+        x_basis, nb, x_post, x_post_stride, nx, mu, mu_idx, Sigma, sig_idx, kernel_const, kernel_length, kernel_noise,
+        f_out, cov_out, work, info);
+    HGP_LAUNCH_CHECK("hgp_pred_dist_inducing");
+    return 0;
+}

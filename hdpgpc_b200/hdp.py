@@ -388,8 +388,9 @@ class GPI_HDP:
     def cluster_new_batch(self, x_trains, y_trains, learning=False, it_limit=None, warp=False):
         if learning or warp:
             raise HgpError("cluster_new_batch(learning=True / warp=True) is outside the built hot path")
-        for gp in self.gpmodels[0]:
-            gp._check_grid(x_trains)
+        if len(self.gpmodels[0]) and self.gpmodels[0][0]._off_grid(x_trains) is not None:
+            raise HgpError("cluster_new_batch on grids other than x_basis goes through GPI_model.compute_sq_err_all; "
+                           "the fused sweep needs x_train == x_basis")
         eng = self.build_engine(y_trains, mode="last")
         out = eng.sweep()
         self.last_sweep = out

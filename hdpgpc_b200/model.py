@@ -153,18 +153,96 @@ class GPI_model:
         if bad.numel():
             raise LinAlgError(f"linalg.cholesky: factor {int(bad[0])} is not positive-definite "
                               f"(leading minor {int(info[bad[0]])})")
-        self._tables = dict(mu=mu, W=W, factor_of_state=inv.astype(np.int32), first_factor=n_u)
+        self._tables = dict(mu=mu, W=W, factor_of_state=inv.astype(np.int32), first_factor=n_u, cidx=cidx)
         return self._tables
 
     # ---- the seam methods ----
-    def _check_grid(self, x_trains):
+    def _off_grid(self, x_trains):
+        """None when every grid equals x_basis (pred_dist short-circuit, GPI.py:467-468); otherwise the grids as a
+        float64 array [n, nx] (n = 1 for a single / shared grid)."""
         if x_trains is None:
-            return
+            return None
         x = x_trains.detach().cpu().numpy() if isinstance(x_trains, torch.Tensor) else np.asarray(x_trains)
-        x = x.reshape(-1, self.T) if x.size % self.T == 0 else None
-        if x is None or not np.all(x == self.x_basis[None, :]):
-            raise HgpError("x_train != x_basis (inducing-point branch, GPI.py:470-501) is not built yet; "
-                           "no CPU fallback")
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 3:
+            x = x[:, :, 0]
+        elif x.ndim == 2 and x.shape[1] == 1:
+            x = x[:, 0][None, :]
+        elif x.ndim == 1:
+            x = x[None, :]
+        if x.shape[1] == self.T and np.all(x == self.x_basis[None, :]):
+            return None
+        return np.ascontiguousarray(x)
+
+    def _state_params(self):
+        """(C index, f_star index) of every state, as GPI_model.observe (:626-662) picks them."""
+        tb = self.tables()
+        return tb["cidx"], tb["mu"]
+
+    def observe(self, x_post, t, params=None, proj=False):
+        """GPI_model.observe (GPI_model.py:626-662): emission distribution of state t resampled on x_post.
+        Returns (mean (nx,), cov (nx, nx)) CUDA tensors."""
+        if proj or params is not None:
+            raise HgpError("observe(proj=True / params=...) is not built")
+        c_i, f_i = self.param_index(int(t))
+        grid = self._off_grid(x_post)
+        tb = self.tables()
+        if grid is None:
+            return tb["mu"][f_i].clone(), self.Sigma[c_i].clone()
+        if self.kernel is None:
+            raise HgpError("observe on a grid other than x_basis needs the fitted kernel (const, length, noise)")
+        dev = self.device
+        one = lambda v: torch.tensor([v], dtype=torch.int32, device=dev)
+        f, cov, info = ops.pred_dist_inducing(torch.from_numpy(self.x_basis).to(dev), torch.from_numpy(grid[0]).to(dev),
+                                              tb["mu"], one(f_i), self.Sigma, one(c_i), self.kernel)
+        if int(info[0]):
+            raise LinAlgError("linalg.cholesky: K(x_basis, x_basis) + jitter is not positive-definite")
+        return f[0], cov[0]
+
+    def _score_off_grid(self, grids, Y, t_idx, first, chunk=256):
+        """Score beats on grids that differ from x_basis: per item pred_dist (kernel matrices, Cholesky, projected
+        covariance), then the Gaussian score under that item's own covariance (GPI_model.py:535-547 / :516-533 with a
+        shared off-basis grid).  grids [1 | n, nx]; Y [n, nx]; t_idx, first: per-beat state index / first flag."""
+        if self.kernel is None:
+            raise HgpError("scoring on a grid other than x_basis needs the fitted kernel (const, length, noise)")
+        dev = self.device
+        tb = self.tables()
+        n = Y.shape[0]
+        pidx = np.array([self.param_index(int(t)) for t in t_idx], dtype=np.int64).reshape(n, 2)
+        first = np.asarray(first, dtype=bool)
+        shared = grids.shape[0] == 1
+        out = torch.empty(n, dtype=F64, device=dev)
+        xb = torch.from_numpy(self.x_basis).to(dev)
+        jit1 = 1e-2 * torch.mean(torch.diagonal(self.Sigma[0]))
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        if shared:
+            # one item per distinct (state, first) group, every beat of the group scored under it
+            key = pidx[:, 0] * (2 * (pidx[:, 1].max() + 1)) + pidx[:, 1] * 2 + first
+            uniq, rep, inv = np.unique(key, return_index=True, return_inverse=True)
+            items = [(rep, inv)]
+            xg = torch.from_numpy(grids[0]).to(dev)
+        else:
+            items = [(np.arange(s, min(s + chunk, n)), None) for s in range(0, n, chunk)]
+        for rep, inv in items:
+            xp = xg if shared else torch.from_numpy(grids[rep]).to(dev)
+            f, cov, info = ops.pred_dist_inducing(xb, xp, tb["mu"], i32(pidx[rep, 1]), self.Sigma, i32(pidx[rep, 0]),
+                                                  self.kernel)
+            if bool(torch.any(info != 0)):
+                raise LinAlgError("linalg.cholesky: K(x_basis, x_basis) + jitter is not positive-definite")
+            add = torch.from_numpy(first[rep].astype(np.float64)).to(dev) * jit1
+            Lf, info = ops.chol_batched(cov, add_diag=add)
+            if bool(torch.any(info != 0)):
+                raise LinAlgError("linalg.cholesky: projected emission covariance is not positive-definite")
+            W = ops.tri_inverse_batched(Lf)
+            k = len(rep)
+            if shared:
+                q = ops.score_pairs(Y, f, W, i32(inv.reshape(n, 1)), i32(np.arange(k)))
+                out[:] = q[:, 0]
+            else:
+                q = ops.score_pairs(Y[rep[0]:rep[-1] + 1].contiguous(), f, W, i32(np.arange(k).reshape(k, 1)),
+                                    i32(np.arange(k)))
+                out[rep[0]:rep[-1] + 1] = q[:, 0]
+        return out
 
     def _beats(self, y_trains):
         y = y_trains
@@ -182,9 +260,15 @@ class GPI_model:
         N = Y.shape[0]
         if self.N == 0:
             return torch.zeros(N, dtype=F64, device=self.device)
-        self._check_grid(x_trains)
-        tb = self.tables()
+        grids = self._off_grid(x_trains)
         i_vals, first = state_index_map(self.indexes, N, no_first)
+        if grids is not None:
+            if grids.shape[0] not in (1, N):
+                raise HgpError("compute_sq_err_all: one grid per beat expected")
+            if grids.shape[0] == N and np.all(grids == grids[0:1]):
+                grids = grids[0:1]          # the reference's shared-grid test (GPI_model.py:516)
+            return self._score_off_grid(grids, Y, i_vals, first)
+        tb = self.tables()
         # `first` beats use a duplicate of state 1 whose factor carries the extra jitter
         fos = np.concatenate([tb["factor_of_state"], [tb["first_factor"]]]).astype(np.int32)
         mu = torch.cat([tb["mu"], tb["mu"][1:2] if tb["mu"].shape[0] > 1 else tb["mu"][0:1]], dim=0)
@@ -197,7 +281,16 @@ class GPI_model:
         """GPI_model.log_sq_error (GPI_model.py:250-286) for params=None; i=None / -1 = last state."""
         if proj:
             raise HgpError("log_sq_error(proj=True) is not built")
-        self._check_grid(x_train)
+        grids = self._off_grid(x_train)
+        if grids is not None:
+            if mean is not None:
+                raise HgpError("log_sq_error with explicit parameters on a grid other than x_basis is not built")
+            Yg = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
+                                                        dtype=np.float64).reshape(1, -1)))
+            nF = self.f_star.shape[0]
+            t = -1 if i is None else i
+            t = t if t >= 0 else nF + t
+            return self._score_off_grid(grids[0:1], Yg, [t], [bool(first)])[0]
         if mean is not None:
             # explicit parameters (estimate_new path, :261-264 -> observe :657-660): mean' = C @ mean, cov = Sigma
             dev = self.device
@@ -277,7 +370,8 @@ class GPI_model:
         Nothing is stored.  Returns (f (T,), cov (T,T))."""
         if t is not None:
             raise HgpError("posterior_weighted(t=...) is not built")
-        self._check_grid(x_train)
+        if self._off_grid(x_train) is not None:
+            raise HgpError("posterior_weighted on a grid other than x_basis is not built; no CPU fallback")
         if not h > 0.0:
             return self.f_star[-1].clone(), self.cov_f[-1].clone()
         T, dev = self.T, self.device
@@ -391,7 +485,8 @@ class GPI_model:
         """GPI_model.full_pass_weighted (GPI_model.py:377-406) for a fresh fitted dynamic model: assimilate the
         beats with resp > 0.99 in time order (Kalman + pair smoother + MNIW per member), full RTS pass, then
         (q, q_lat) over all beats.  One persistent CTA runs the whole chain on the device."""
-        self._check_grid(x_trains)
+        if self._off_grid(x_trains) is not None:
+            raise HgpError("full_pass_weighted on a grid other than x_basis is not built; no CPU fallback")
         Y = self._beats(y_trains)
         desc = self._chain_prepare(Y, resp)
         if desc is None:

@@ -215,6 +215,34 @@ def la_op(op, A, B=None, C=None, T=None):
     return int(info)
 
 
+def pred_dist_inducing(x_basis, x_post, mu, mu_idx, Sigma, sig_idx, kernel):
+    """IterativeGaussianProcess.pred_dist kernel branch (GPI.py:470-501) for a batch of (grid, state) items.
+    x_basis [nb]; x_post [n_items, nx] or [nx] (one shared grid); mu [*, nb]; Sigma [*, nb, nb]; kernel = (const,
+    length, noise).  Returns (f [n_items, nx], cov [n_items, nx, nx], info [n_items])."""
+    lib = _lib_ready()
+    xb = _dev(x_basis).to(F64).contiguous()
+    xp = _dev(x_post).to(F64).contiguous()
+    mu_idx = _dev(mu_idx).to(I32).contiguous()
+    sig_idx = _dev(sig_idx).to(I32).contiguous()
+    n_items = mu_idx.numel()
+    nb = xb.numel()
+    shared = xp.dim() == 1
+    nx = xp.shape[-1]
+    if not shared and xp.shape[0] != n_items:
+        raise _lib.HgpError("pred_dist_inducing: one grid per item expected")
+    mu = _dev(mu).contiguous()
+    Sigma = _dev(Sigma).contiguous()
+    f = torch.empty((n_items, nx), dtype=F64, device=xb.device)
+    cov = torch.empty((n_items, nx, nx), dtype=F64, device=xb.device)
+    info = torch.zeros(n_items, dtype=I32, device=xb.device)
+    work = torch.empty(int(lib.hgp_pred_dist_work_doubles(n_items, nb, nx)), dtype=F64, device=xb.device)
+    c, ell, noise = (float(v) for v in kernel)
+    check(lib.hgp_pred_dist_inducing(ptr(xb), nb, ptr(xp), 0 if shared else nx, nx, ptr(mu), ptr(mu_idx), ptr(Sigma),
+                                     ptr(sig_idx), n_items, c, ell, noise, ptr(f), ptr(cov), ptr(work), ptr(info),
+                                     stream_ptr()), "hgp_pred_dist_inducing")
+    return f, cov, info
+
+
 def chain_run(descs, T):
     """descs: list of dicts with the fields of hgp_chain_desc (tensors or scalars).  Runs all chains in one launch."""
     import ctypes as _ct

@@ -178,6 +178,19 @@ int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream);
 /* Unit-test hook for the CTA-level routines the chain kernel is built from (gemm variants, chol, trsm, LU solve). */
 int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream);
 
+/* ---- emission distribution on a grid other than the basis grid: IterativeGaussianProcess.pred_dist
+ *      (GPI.py:457-503, kernel branch :470-501; reached from GPI_model.observe :626-662 when x_train != x_basis)
+ * Per item: kernel matrices K_bb, K_bx, K_xx of ConstantKernel(c)*RBF(l) (+ WhiteKernel(noise) on K_xx only),
+ * L = chol(K_bb + 1e-4 mean|diag Sigma| I), W = K_bb^{-1} K_bx, f* = W^T mu,
+ * cov = mean(diag Sigma) I if Sigma has a constant diagonal, else sym(K_xx - K_bx^T W + W^T Sigma W) + 1e-6 I.
+ * x_post: [n_items] grids of nx points (stride x_post_stride doubles; 0 = one shared grid);
+ * mu: rows of nb (emission means C f on the basis grid), Sigma: nb x nb stacks, both gathered by index. */
+int64_t hgp_pred_dist_work_doubles(int64_t n_items, int nb, int nx);
+int hgp_pred_dist_inducing(const double* x_basis, int nb, const double* x_post, int64_t x_post_stride, int nx,
+                           const double* mu, const int* mu_idx, const double* Sigma, const int* sig_idx,
+                           int64_t n_items, double kernel_const, double kernel_length, double kernel_noise,
+                           double* f_out, double* cov_out, double* work, int* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

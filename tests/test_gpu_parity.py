@@ -227,6 +227,61 @@ def test_online_extras_vs_reference(golden):
         assert len(means) == gp.f_star.shape[0] + 1 and means[-1].shape == (Y.shape[1],)
 
 
+def test_inducing_grid_vs_reference(golden):
+    """x_train != x_basis: kernel-matrix construction, Cholesky, projection and score on the device
+    against GPI_model.observe / log_sq_error outputs of the reference (IterativeGaussianProcess.pred_dist kernel branch,
+    GPI.py:470-501), plus the irregular-grid fallback of compute_sq_err_all (GPI_model.py:535-547) against the oracle."""
+    import hdpgpc_b200 as hb
+    z = golden("inducing_T30")
+    gp = hb.GPI_model.from_dump(z, "gp_")
+    og = O.OracleGP.from_dump(z, "gp_")
+    Y = z["data"][:, :, 0]
+    x_off, x_sub = z["x_off"].reshape(-1), z["x_sub"].reshape(-1)
+    for k, i in enumerate([1, 4, 9]):
+        f, c = gp.observe(x_off, i)
+        ref_f, ref_c = z[f"obs_off_{i}_mean"][:, 0], z[f"obs_off_{i}_cov"]
+        assert np.max(np.abs(f.cpu().numpy() - ref_f)) < 1e-8 * np.max(np.abs(ref_f))
+        assert np.max(np.abs(c.cpu().numpy() - ref_c)) < 1e-8 * np.max(np.abs(ref_c))
+        s = [float(gp.log_sq_error(x_off, Y[n], i=i)) for n in range(6)]
+        assert rel(s, z["score_off"][k]) < TOL
+    assert rel([float(gp.log_sq_error(x_off, Y[n], i=-1)) for n in range(6)], z["score_off_last"]) < TOL
+    # fewer points than the basis (nx = 15 < nb = 30)
+    f, c = gp.observe(x_sub, 3)
+    assert np.max(np.abs(c.cpu().numpy() - z["obs_sub_3_cov"])) < 1e-8 * np.max(np.abs(z["obs_sub_3_cov"]))
+    assert rel([float(gp.log_sq_error(x_sub, Y[n, ::2], i=3)) for n in range(6)], z["score_sub"]) < TOL
+    # on-grid short-circuit returns the stored state
+    f, c = gp.observe(z["x_basis"], 4)
+    fo, co = og.observe(z["x_basis"].reshape(-1), 4)
+    assert rel(f, fo) < 1e-12 and np.max(np.abs(c.cpu().numpy() - co)) == 0.0
+    # all beats: a shared off-basis grid (group path) and per-beat jittered grids (irregular fallback)
+    N, T = Y.shape
+    q = gp.compute_sq_err_all(np.repeat(x_off[None, :, None], N, axis=0), Y[:, :, None])
+    want = og.compute_sq_err_all(np.repeat(x_off[None, :], N, axis=0), Y)
+    assert rel(q, want) < TOL
+    rng = np.random.default_rng(3)
+    grids = z["x_basis"].reshape(1, -1) + rng.uniform(-0.3, 0.3, size=(N, T))
+    q = gp.compute_sq_err_all(grids[:, :, None], Y[:, :, None])
+    i_vals, first = og.state_index_map(N)
+    want = np.array([og.log_sq_error(grids[n], Y[n], i=int(i_vals[n]), first=bool(first[n])) for n in range(N)])
+    assert rel(q, want) < TOL
+    qn = gp.compute_sq_err_all(grids[:, :, None], Y[:, :, None], no_first=True)
+    assert float(torch.max(torch.abs(qn - q))) > 0.0 and rel(qn[~first], want[~first]) < TOL
+
+
+def test_inducing_constant_diagonal_shortcut(golden):
+    """cov = mean(diag Sigma) I when Sigma has a constant diagonal (GPI.py:497-498): prior state of a fresh model."""
+    import hdpgpc_b200 as hb
+    z = golden("inducing_T30")
+    T = z["x_basis"].shape[0]
+    kern = z["gp_kernel"]
+    gp = hb.GPI_model(z["x_basis"], z["gp_f_star"][:1], z["gp_f_star_sm"][:1], z["gp_C"][:1],
+                      np.eye(T)[None] * z["gp_Sigma"][0][0, 0], [], kernel=kern)
+    f, c = gp.observe(z["x_off"], 0)
+    want = np.eye(T) * z["gp_Sigma"][0][0, 0]
+    assert np.max(np.abs(c.cpu().numpy() - want)) < 1e-14 * want[0, 0]
+    assert np.max(np.abs(z["obs_prior_cov"] - np.eye(T) * z["obs_prior_cov"][0, 0])) == 0.0   # the reference's shape
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
