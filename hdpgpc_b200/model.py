@@ -102,9 +102,12 @@ class GPI_model:
     def from_dump(cls, z, prefix, device="cuda"):
         """From a tests/golden fixture written by generate_golden.dump_gp(full=True)."""
         g = lambda k: z[prefix + k]
-        return cls(g("x_basis"), g("f_star"), g("f_star_sm"), g("C"), g("Sigma"), g("indexes"),
+        self = cls(g("x_basis"), g("f_star"), g("f_star_sm"), g("C"), g("Sigma"), g("indexes"),
                    estimation_limit=float(g("estimation_limit")), A=g("A"), Gamma=g("Gamma"),
                    cov_f_sm=g("cov_f_sm"), cov_f=g("cov_f"), kernel=g("kernel"), device=device)
+        if prefix + "A_def" in z:
+            self.defaults = {k: _stack(g(k + "_def")[None], self.device)[0] for k in ("A", "Gamma", "C", "Sigma")}
+        return self
 
     # ---- index rules (host integer work) ----
     def find_closest_lower(self, t):
@@ -363,6 +366,18 @@ class GPI_model:
         out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals
         return out
 
+    # ---- ELBO term of the LDS parameters -----------------------------------------------------------
+    def _prior_defaults(self):
+        """(A_def, Gamma_def, C_def, Sigma_def): the prior the chain started from (GPI_model.py:466)."""
+        d = getattr(self, "defaults", None)
+        if d is None:
+            d = dict(A=self.A[0], Gamma=self.Gamma[0], C=self.C[0], Sigma=self.Sigma[0])
+        return d
+
+    def return_LDS_param_likelihood(self, first=False):
+        """GPI_model.return_LDS_param_likelihood (GPI_model.py:459-486), first=False."""
+        return lds_param_likelihood_batch([self], first=first)[0]
+
     # ---- online extras ------------------------------------------------------------------------------
     def posterior_weighted(self, x_train, y, h, t=None):
         """GPI_model.posterior_weighted (GPI_model.py:561-582), t=None: one Kalman update
@@ -520,3 +535,35 @@ def full_pass_weighted_batch(models, Y_planes, resp):
         q[:, m, ld] = gp.compute_sq_err_all(None, Y_planes[ld])
         q_lat[:, m, ld] = gp.compute_q_lat_all(Y_planes[ld])
     return q, q_lat
+
+
+def lds_param_likelihood_batch(models, first=False):
+    """GPI_model.return_LDS_param_likelihood (GPI_model.py:459-486) for a list of models in one batched call:
+    MNIW log-likelihood of (A[-1], Gamma[-1]) under MNIW(A_def, I, Gamma_def) (skipped when Gamma_def is all zero) plus
+    that of (C[-1], Sigma[-1]) under MNIW(C_def, I, Sigma_def), times 100 / T.  Returns a float64 CUDA tensor [len]."""
+    if first:
+        raise HgpError("return_LDS_param_likelihood(first=True) is not built (unused by the reference's drivers)")
+    if not models:
+        return torch.zeros(0, dtype=F64)
+    dev, T = models[0].device, models[0].T
+    mats, owner, use = [], [], []
+    eye = torch.eye(T, dtype=F64, device=dev)
+    for k, gp in enumerate(models):
+        d = gp._prior_defaults()
+        pairs = [(gp.C[-1], gp.Sigma[-1], d["C"], d["Sigma"])]
+        if bool(torch.any(d["Gamma"] != 0)):
+            pairs.append((gp.A[-1], gp.Gamma[-1], d["A"], d["Gamma"]))
+        for M_, S_, pm, ps in pairs:
+            mats.append((M_, S_, pm, ps))
+            owner.append(k)
+    J = len(mats)
+    stack = lambda i: torch.stack([m[i] for m in mats], dim=0)
+    ar = torch.arange(J, dtype=torch.int32, device=dev)
+    zero = torch.zeros(J, dtype=torch.int32, device=dev)
+    vals, info = ops.mniw_loglik_batched(stack(0), ar, stack(1), ar, stack(2), ar, eye[None], zero, stack(3), ar)
+    bad = torch.nonzero(info).flatten()
+    if bad.numel():
+        raise LinAlgError(f"linalg.cholesky: LDS noise covariance of model {owner[int(bad[0])]} is not positive-definite")
+    out = torch.zeros(len(models), dtype=F64, device=dev)
+    out.index_add_(0, torch.as_tensor(owner, device=dev, dtype=torch.long), vals)
+    return out / T * 100

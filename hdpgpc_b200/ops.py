@@ -262,3 +262,74 @@ def chain_run(descs, T):
     check(lib.hgp_chain_run(ptr(dev), n, T, stream_ptr()), "hgp_chain_run")
     torch.cuda.current_stream().synchronize()
     return keep
+
+
+def warp_fit_batched(x_model, Y, y_model, noise, lam_s, lam_a, n_ctrl=8, lr=5e-2, train_iter=50, u0=None,
+                     grad_scale=None, want_u=False, want_trace=False):
+    """Warping_system.compute_warp_batch's optimisation (amtgp_warping_system.py:548-736) for every (beat, template)
+    pair.  Y [N, T], y_model [R, T] -> x_warp, y_warp [R, N, T] (+ u [R, N, n_ctrl], loss trace [iters, R, N])."""
+    lib = _lib_ready()
+    x = _dev(x_model).to(F64).contiguous()
+    Y = _dev(Y).to(F64).contiguous()
+    Ym = _dev(y_model).to(F64).contiguous().reshape(-1, Y.shape[1])
+    N, T = Y.shape
+    R = Ym.shape[0]
+    dev = Y.device
+    xw = torch.empty((R, N, T), dtype=F64, device=dev)
+    yw = torch.empty((R, N, T), dtype=F64, device=dev)
+    u = torch.empty((R, N, n_ctrl), dtype=F64, device=dev) if want_u else None
+    tr = torch.empty((train_iter, R, N), dtype=F64, device=dev) if want_trace else None
+    if u0 is not None:
+        u0 = _dev(u0).to(F64).contiguous().reshape(R, n_ctrl)
+    if grad_scale is not None:
+        grad_scale = _dev(grad_scale).to(F64).contiguous()
+        if grad_scale.numel() != N:
+            raise _lib.HgpError("warp_fit_batched: grad_scale must have one entry per beat")
+    check(lib.hgp_warp_fit_batched(ptr(x), T, ptr(Y), N, ptr(Ym), R, ptr(u0), int(n_ctrl), int(train_iter), float(lr),
+                                   float(noise), float(lam_s), float(lam_a), ptr(grad_scale), ptr(xw), ptr(yw), ptr(u),
+                                   ptr(tr), stream_ptr()), "hgp_warp_fit_batched")
+    return xw, yw, u, tr
+
+
+def warp_prior_factor(x_model, rho, omega, diag_add, normalize_x=True):
+    """Cholesky of the warp-prior covariance (WarpPriorAMTGP._ensure_cache, amtgp_warping_system.py:175-194):
+    returns (W = L^-1 [1, T, T], logdet 0-d tensor)."""
+    lib = _lib_ready()
+    x = _dev(x_model).to(F64).contiguous()
+    T = x.numel()
+    K = torch.empty((1, T, T), dtype=F64, device=x.device)
+    check(lib.hgp_warp_prior_cov(ptr(x), T, float(rho), float(omega), float(diag_add), int(bool(normalize_x)), ptr(K),
+                                 stream_ptr()), "hgp_warp_prior_cov")
+    Lf, info, logdet = chol_batched(K, jitter_scale=0.0, want_logdet=True)
+    if int(info[0]):
+        raise _lib.HgpError("warp prior covariance is not positive-definite")
+    return tri_inverse_batched(Lf), logdet[0]
+
+
+def warp_prior_score(W, logdet, x_warp):
+    """WarpPriorAMTGP.log_sq_error_batch (:223-264): -0.5 (w^T K^-1 w + logdet + T log 2 pi) for rows of x_warp [B, T]."""
+    xw = _dev(x_warp).to(F64).contiguous()
+    B, T = xw.shape
+    dev = xw.device
+    zero_mu = torch.zeros((1, T), dtype=F64, device=dev)
+    q = score_pairs(xw, zero_mu, W, torch.zeros((B, 1), dtype=I32, device=dev), torch.zeros(1, dtype=I32, device=dev))
+    return q[:, 0] - 0.5 * logdet
+
+
+def mniw_loglik_batched(M, M_idx, Sigma, S_idx, prior_mean, pm_idx, prior_rcov, pr_idx, prior_scale, ps_idx):
+    """matrix_normal_inv_wishart.log_likelihood_MNIW (GPI_model.py:1346-1362) for J (parameter, prior) items selected by
+    index from stacked [*, T, T] inputs.  Returns (out [J], info [J])."""
+    lib = _lib_ready()
+    T = M.shape[-1]
+    dev = M.device
+    idx = [_dev(i).to(I32).contiguous() for i in (M_idx, S_idx, pm_idx, pr_idx, ps_idx)]
+    J = idx[0].numel()
+    mats = [_dev(m).to(F64).contiguous() for m in (M, Sigma, prior_mean, prior_rcov, prior_scale)]
+    out = torch.empty(J, dtype=F64, device=dev)
+    info = torch.zeros(J, dtype=I32, device=dev)
+    need = int(lib.hgp_mniw_workspace_bytes(J, T))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib.hgp_mniw_loglik_batched(ptr(mats[0]), ptr(idx[0]), ptr(mats[1]), ptr(idx[1]), ptr(mats[2]), ptr(idx[2]),
+                                      ptr(mats[3]), ptr(idx[3]), ptr(mats[4]), ptr(idx[4]), J, T, ptr(out), ptr(info),
+                                      ptr(ws), need, stream_ptr()), "hgp_mniw_loglik_batched")
+    return out, info

@@ -191,6 +191,38 @@ int hgp_pred_dist_inducing(const double* x_basis, int nb, const double* x_post, 
                            int64_t n_items, double kernel_const, double kernel_length, double kernel_noise,
                            double* f_out, double* cov_out, double* work, int* info, void* stream);
 
+/* ---- MNIW log-likelihood of LDS parameters under the prior: matrix_normal_inv_wishart.log_likelihood_MNIW
+ *      (GPI_model.py:1346-1362), the per-cluster ELBO term of return_LDS_param_likelihood (:459-486) ----
+ * For j in [0, J):  L = chol(sym(Sigma[S_idx[j]]) + 1e-8 I);  D = M[M_idx[j]] - prior_mean[pm_idx[j]]
+ *   out[j] = -0.5 sum((D R) (.) Sigma^{-1} D) - 0.5 tr(Sigma^{-1} S),  R = prior_rcov[pr_idx[j]], S = prior_scale[ps_idx[j]]
+ * computed with W = L^{-1} as sum((X R) (.) X), X = W D, and sum((W S) (.) W) on the FP64 tensor cores. */
+int64_t hgp_mniw_workspace_bytes(int64_t J, int T);
+int hgp_mniw_loglik_batched(const double* M, const int* M_idx, const double* Sigma, const int* S_idx,
+                            const double* prior_mean, const int* pm_idx, const double* prior_rcov, const int* pr_idx,
+                            const double* prior_scale, const int* ps_idx, int64_t J, int T, double* out, int* info,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- batched alignment ("warp"): Warping_system.compute_warp_batch (amtgp_warping_system.py:548-736), D = 1.
+ * Fits, for every (beat n, representative r) pair, the monotone warp g(t) (n_ctrl control values -> linear expansion ->
+ * softplus -> cumulative sum -> [x_min, x_max]) with `train_iter` Adam(lr) steps on
+ *   grad_scale[n] * (0.5 |y_n(g) - y_model_r|^2 / (noise + 1e-12) + lam_s |D2 (g - x)|^2 + lam_a |g - x|^2)
+ * (grad_scale[n] = weight_n / (sum of weights of the reference's batch + 1e-12): the reference optimises the batch
+ * mean, and Adam's epsilon makes the scale observable).  One warp per fit; closed-form gradient.
+ * x_model [T]; Y [N][T]; y_model [R][T]; u0 [R][n_ctrl] warm start or NULL (zeros); grad_scale [N] or NULL (ones).
+ * Outputs x_warp, y_warp [R][N][T] (g - x and the beat resampled on g); u_out [R][N][n_ctrl] or NULL;
+ * loss_trace [train_iter][R][N] (unscaled loss before each step) or NULL. */
+int hgp_warp_fit_batched(const double* x_model, int T, const double* Y, int64_t N, const double* y_model, int R,
+                         const double* u0, int n_ctrl, int train_iter, double lr, double noise, double lam_s,
+                         double lam_a, const double* grad_scale, double* x_warp, double* y_warp, double* u_out,
+                         double* loss_trace, void* stream);
+
+/* Covariance of the GP prior on warps: WarpPriorAMTGP._rbf_cov (amtgp_warping_system.py:160-173):
+ * K = omega^2 exp(-0.5 (dx / rho)^2) + diag_add I on the grid normalised to [0, 1] when normalize_x != 0.
+ * The prior score log_sq_error_batch (:223-264) is then hgp_chol_batched (log-det) + hgp_tri_inverse_batched +
+ * hgp_score_pairs with a zero mean. */
+int hgp_warp_prior_cov(const double* x, int T, double rho, double omega, double diag_add, int normalize_x, double* K,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

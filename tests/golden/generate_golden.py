@@ -370,6 +370,60 @@ def online_extras():
     print(f"online_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def warp_scenario():
+    """Batched alignment: Warping_system.compute_warp_batch (amtgp_warping_system.py:548-736),
+    WarpPriorAMTGP.log_sq_error_batch (:223-264) and the cached driver GPI_HDP.warp_batch_by_resp_amtgp_cached
+    (GPI_HDP.py:3412-3517) on record 102 (the record test_offline.py warps), lead 0, T=90."""
+    N = 150
+    data, labels = load_record("102", N, [0], 1)
+    sw, x_trains, x_basis, hyper = make_model(data)
+    sw.warp = True
+    out = dict(data=data, x_basis=x_basis)
+    xt = torch.from_numpy(x_trains)
+    yt = torch.from_numpy(data)
+    T = data.shape[1]
+    # direct batch fit: 40 beats against beat 3, default (theta float -> base lambdas) and tuple theta
+    warper = sw.wp_sys[0][0]
+    x0 = xt[3]
+    noise_vec = np.sqrt(sw.ini_sigma_def) * torch.ones(T, dtype=torch.float64)
+    for tag, theta in (("f", sw.kernel_def.get_params()["k1__k2__length_scale"]), ("t", (2.0, 0.5))):
+        xw, yw, lik, trace = warper.compute_warp_batch(x0, yt[:40, :, [0]], yt[3, :, [0]], theta=theta, noise=noise_vec,
+                                                       train_iter=50)
+        out[f"fit_{tag}_xw"] = npy(xw)[:, :, 0]
+        out[f"fit_{tag}_yw"] = npy(yw)[:, :, 0]
+        out[f"fit_{tag}_lik"] = npy(lik)
+        out[f"fit_{tag}_trace"] = np.array([trace[k] for k in ("loss", "data", "smooth", "amp")])
+    out["fit_t_theta"] = np.array([2.0, 0.5])
+    out["noise"] = np.float64(np.sqrt(sw.ini_sigma_def))
+    out["noise_warp"] = np.float64(warper.noise_warp_default)
+    out["noise_bounds"] = np.array(warper.noise_bounds, dtype=np.float64)
+    out["theta_float"] = np.float64(sw.kernel_def.get_params()["k1__k2__length_scale"])
+    out["n_ctrl"] = np.int64(warper.n_ctrl)
+    out["lr"] = np.float64(warper.lr)
+    # the cached driver: two clusters with representative beats 3 and 77, all N beats in chunks of 128
+    sw2, _, _, _ = make_model(data)
+    sw2.warp = True
+    sw2.M = 2
+    sw2.f_ind_old = torch.tensor([3, 77])
+    while len(sw2.wp_sys[0]) < 2:
+        sw2.wp_sys[0].append(sw2.create_warp_default() if hasattr(sw2, "create_warp_default") else sw2.wp_sys[0][0])
+    resp = torch.zeros(N, 2, dtype=torch.float64)
+    resp[:, 0] = 1.0
+    yw4, xw4, liks = sw2.warp_batch_by_resp_amtgp_cached(xt, yt, resp)
+    out["drv_f_ind"] = np.array([3, 77])
+    out["drv_yw"] = npy(yw4)      # (N, T, 1, 2)
+    out["drv_xw"] = npy(xw4)
+    out["drv_liks"] = npy(liks)   # (N, 2, 1)
+    bw = sw2.wp_sys[0][-1]
+    out["drv_base_noise_warp"] = np.float64(bw.warp_gp.noise_warp)
+    out["drv_base_noise_bounds"] = np.array(bw.warp_gp.noise_bounds, dtype=np.float64)
+    out["drv_fit_noise_warp"] = np.array([w.warp_gp.noise_warp for w in sw2.wp_sys[0][:2]])
+    out["drv_fit_noise_bounds"] = np.array([w.warp_gp.noise_bounds for w in sw2.wp_sys[0][:2]], dtype=np.float64)
+    path = os.path.join(HERE, "warp_rec102_T90.npz")
+    np.savez_compressed(path, **out)
+    print(f"warp_rec102_T90 -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 SCENARIOS = {
     # full state dumps at T=30 (every 3rd sample of the bundled T=90 beats keeps fixtures small)
     "offline_rec100_T30_L1": lambda: offline_scenario("offline_rec100_T30_L1", "100", 40, [0], 3, 24, True),
@@ -379,6 +433,7 @@ SCENARIOS = {
     "hmm_synth": hmm_synth,
     "inducing_T30": inducing,
     "online_T30": online_extras,
+    "warp_rec102_T90": warp_scenario,
 }
 
 if __name__ == "__main__":

@@ -282,6 +282,99 @@ def test_inducing_constant_diagonal_shortcut(golden):
     assert np.max(np.abs(z["obs_prior_cov"] - np.eye(T) * z["obs_prior_cov"][0, 0])) == 0.0   # the reference's shape
 
 
+def test_warp_fit_vs_reference(golden):
+    """Batched alignment on the device against the reference's autograd + Adam outputs:
+    Warping_system.compute_warp_batch (amtgp_warping_system.py:548-736) with a float theta (base lambdas) and a tuple
+    theta, the warp-prior score (:223-264), and the chunked all-beats driver (GPI_HDP.py:3412-3517)."""
+    from hdpgpc_b200 import warp as hw
+    z = golden("warp_rec102_T90")
+    x = z["x_basis"].reshape(-1)
+    Y = z["data"][:, :, 0]
+    T = x.size
+    mk = lambda: hw.Warping_system(np.arange(0, T, 2.0), float(z["noise_warp"]), tuple(z["noise_bounds"]), recursive=False)
+    noise_vec = np.full(T, float(z["noise"]))
+    for tag, theta in (("f", float(z["theta_float"])), ("t", tuple(z["fit_t_theta"]))):
+        ws = mk()
+        xw, yw, lik, trace = ws.compute_warp_batch(x, Y[:40, :, None], Y[3][:, None], theta=theta, noise=noise_vec)
+        assert xw.shape == (40, T, 1) and yw.shape == (40, T, 1) and lik.shape == (40,)
+        ref_xw, ref_yw = z[f"fit_{tag}_xw"], z[f"fit_{tag}_yw"]
+        assert np.max(np.abs(xw[:, :, 0].cpu().numpy() - ref_xw)) < TOL * np.max(np.abs(ref_xw))
+        assert np.max(np.abs(yw[:, :, 0].cpu().numpy() - ref_yw)) < TOL * np.max(np.abs(ref_yw))
+        assert rel(lik, z[f"fit_{tag}_lik"]) < TOL
+        assert rel(trace["loss"], z[f"fit_{tag}_trace"][0]) < TOL
+    ws = [mk(), mk()]
+    yw, xw, liks = hw.warp_batch_by_resp(cu(x), cu(Y), z["drv_f_ind"], ws, ws[-1], float(z["theta_float"]), noise_vec)
+    for m in range(2):
+        assert np.max(np.abs(xw[:, :, m].cpu().numpy() - z["drv_xw"][:, :, 0, m])) < TOL * np.max(np.abs(z["drv_xw"][..., m]))
+        assert np.max(np.abs(yw[:, :, m].cpu().numpy() - z["drv_yw"][:, :, 0, m])) < TOL * np.max(np.abs(z["drv_yw"][..., m]))
+        assert rel(liks[:, m], z["drv_liks"][:, m, 0]) < TOL
+
+
+@pytest.mark.parametrize("T,n_ctrl,B", [(256, 8, 37), (17, 4, 5), (64, 16, 130), (33, 8, 1)])
+def test_warp_fit_vs_oracle(T, n_ctrl, B):
+    """Other shapes (T not a multiple of 32, ragged batch, more control points), a non-uniform grid, per-beat weights
+    and a warm start, against the CPU restatement."""
+    from hdpgpc_b200 import ops
+    from oracle import warp_oracle as W
+    rng = np.random.default_rng(T * 1000 + B)
+    x = np.cumsum(rng.uniform(0.5, 1.5, size=T))
+    c = rng.uniform(x[0], x[-1], size=(B, 1))
+    Y = 100.0 * np.exp(-0.5 * ((x[None, :] - c) / (0.08 * (x[-1] - x[0]))) ** 2) + rng.normal(size=(B, T))
+    Ym = 100.0 * np.exp(-0.5 * ((x - x.mean()) / (0.08 * (x[-1] - x[0]))) ** 2)
+    wgt = rng.uniform(0.1, 2.0, size=B)
+    u0 = rng.normal(size=n_ctrl) * 0.3
+    want = W.fit_warp_batch(x, Y, Ym, 0.7, 50.0, 1e-2, n_ctrl, 5e-2, 30, u0=u0, weights=wgt)
+    scale = wgt / (np.sum(wgt) + 1e-12)
+    xw, yw, u, tr = ops.warp_fit_batched(cu(x), cu(Y), cu(Ym[None]), 0.7, 50.0, 1e-2, n_ctrl, 5e-2, 30, u0=cu(u0[None]),
+                                         grad_scale=cu(scale), want_u=True, want_trace=True)
+    assert np.max(np.abs(u[0].cpu().numpy() - want["u"])) < TOL * np.max(np.abs(want["u"]))
+    assert np.max(np.abs(xw[0].cpu().numpy() - want["xw"])) < TOL * np.max(np.abs(want["xw"]))
+    assert np.max(np.abs(yw[0].cpu().numpy() - want["yw"])) < TOL * np.max(np.abs(want["yw"]))
+    assert rel((tr[:, 0, :] @ cu(scale)), want["trace"]["loss"]) < TOL
+    # monotone: g = x + x_warp is non-decreasing and spans the grid
+    g = xw[0].cpu().numpy() + x[None, :]
+    assert np.all(np.diff(g, axis=1) > 0) and np.allclose(g[:, 0], x[0]) and np.allclose(g[:, -1], x[-1])
+    fac, logdet = ops.warp_prior_factor(cu(x), 0.5, 1.3, 0.2 + 1e-6)
+    lik = ops.warp_prior_score(fac, logdet, xw[0])
+    assert rel(lik, W.warp_prior_score(x, want["xw"], 0.2, (1e-8, 1e2), (0.5, 1.3))) < TOL
+
+
+@pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2"])
+def test_lds_param_likelihood_vs_reference(golden, name):
+    """MNIW log-likelihood of every cluster's LDS parameters (full_LDS_elbo ->
+    return_LDS_param_likelihood -> log_likelihood_MNIW, GPI_model.py:459-486 / :1346-1362) against the reference."""
+    import hdpgpc_b200 as hb
+    from hdpgpc_b200.model import lds_param_likelihood_batch
+    z = golden(name)
+    M, L = int(z["M"]), int(z["L"])
+    for ld in range(L):
+        gps = [hb.GPI_model.from_dump(z, f"gp_{ld}_{m}_") for m in range(M)]
+        lik = lds_param_likelihood_batch(gps)
+        assert rel(lik, z["lds_param_lik"][ld]) < TOL
+        assert abs(float(gps[0].return_LDS_param_likelihood()) - z["lds_param_lik"][ld][0]) < TOL * abs(z["lds_param_lik"][ld][0])
+        # GPI_HDP.full_LDS_elbo (GPI_HDP.py:1838-1864): sum over non-empty clusters of lik * N_m / N, over their count
+        Nm = z["train_Nm"]
+        elb = float(torch.sum(lik[cu(Nm) > 0] * cu(Nm / Nm.sum())[cu(Nm) > 0]) / int(np.sum(Nm > 0)))
+        assert abs(elb - z["elbo_full_LDS"][ld]) < TOL * abs(z["elbo_full_LDS"][ld])
+
+
+@pytest.mark.parametrize("T", [9, 64, 90, 200])
+def test_mniw_loglik_vs_oracle(T):
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(T)
+    J = 5
+    Sig = random_spd(rng, J, T, cond=1e4)
+    scale = random_spd(rng, J, T, cond=1e2)
+    rcov = random_spd(rng, 2, T, cond=10.0)
+    Mm = rng.standard_normal((J, T, T)) * 0.1 + np.eye(T)
+    pm = rng.standard_normal((J, T, T)) * 0.05 + np.eye(T)
+    ar = torch.arange(J, dtype=torch.int32, device="cuda")
+    ri = torch.tensor([0, 1, 0, 1, 1], dtype=torch.int32, device="cuda")
+    out, info = ops.mniw_loglik_batched(cu(Mm), ar, cu(Sig), ar, cu(pm), ar, cu(rcov), ri, cu(scale), ar)
+    want = [O.MNIW(pm[j], rcov[int(ri[j])], 5.0, scale[j]).log_likelihood(Mm[j], Sig[j]) for j in range(J)]
+    assert int(torch.count_nonzero(info)) == 0 and rel(out, want) < TOL
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")

@@ -158,3 +158,30 @@ def test_online_extras(golden):
         m, P = gp.posterior_weighted(None, Y[25], 0.5)
         assert np.max(np.abs(m - z[tag + "_post_mean_h05"][:, 0])) < 1e-9 * np.max(np.abs(m))
         assert np.max(np.abs(P - z[tag + "_post_cov_h05"])) < 1e-9 * np.max(np.abs(P))
+
+
+def test_warp_oracle_vs_reference(golden):
+    """Closed-form-gradient restatement of Warping_system.compute_warp_batch + WarpPriorAMTGP.log_sq_error_batch +
+    the chunked driver (GPI_HDP.py:3412-3517) against the reference's autograd/Adam outputs (record 102, T=90)."""
+    from oracle import warp_oracle as W
+    z = golden("warp_rec102_T90")
+    x = z["x_basis"].reshape(-1)
+    Y = z["data"][:, :, 0]
+    nb = z["noise_bounds"]
+    n = float(np.clip(z["noise"], nb[0], nb[1]))
+    for tag, theta in (("f", float(z["theta_float"])), ("t", tuple(z["fit_t_theta"]))):
+        ls, la = W.theta_to_lambdas(theta)
+        r = W.fit_warp_batch(x, Y[:40], Y[3], n, ls, la, int(z["n_ctrl"]), float(z["lr"]), 50)
+        assert np.max(np.abs(r["xw"] - z[f"fit_{tag}_xw"])) < 1e-10 * np.max(np.abs(z[f"fit_{tag}_xw"]))
+        assert np.max(np.abs(r["yw"] - z[f"fit_{tag}_yw"])) < 1e-10 * np.max(np.abs(z[f"fit_{tag}_yw"]))
+        tr = np.array([r["trace"][k] for k in ("loss", "data", "smooth", "amp")])
+        assert rel(tr[:2], z[f"fit_{tag}_trace"][:2]) < 1e-10
+        lik = W.warp_prior_score(x, r["xw"], float(z["noise_warp"]), nb, theta)
+        assert rel(lik, z[f"fit_{tag}_lik"]) < 1e-10
+    for m, ref in enumerate(z["drv_f_ind"]):
+        xw, yw, lik = W.warp_all_beats(x, Y, Y[ref], np.full(x.size, z["noise"]), float(z["drv_fit_noise_warp"][m]),
+                                       z["drv_fit_noise_bounds"][m], float(z["drv_base_noise_warp"]),
+                                       z["drv_base_noise_bounds"], theta=float(z["theta_float"]))
+        assert np.max(np.abs(xw - z["drv_xw"][:, :, 0, m])) < 1e-10 * np.max(np.abs(z["drv_xw"][:, :, 0, m]))
+        assert np.max(np.abs(yw - z["drv_yw"][:, :, 0, m])) < 1e-10 * np.max(np.abs(z["drv_yw"][:, :, 0, m]))
+        assert rel(lik, z["drv_liks"][:, m, 0]) < 1e-10
