@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libhdpgpc_b200.so")
-SOURCES = ["hgp_api.cu", "hgp_linalg.cu", "hgp_score.cu", "hgp_hmm.cu", "hgp_qlat.cu", "hgp_chain.cu", "hgp_warp.cu"]
+SOURCES = ["hgp_api.cu", "hgp_linalg.cu", "hgp_score.cu", "hgp_hmm.cu", "hgp_qlat.cu", "hgp_chain.cu", "hgp_warp.cu", "hgp_hyperfit.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

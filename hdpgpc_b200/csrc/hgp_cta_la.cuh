@@ -85,7 +85,7 @@ __device__ __forceinline__ void la_rank1(double* A, double s, const double* u, c
 // ---- GEMM on the tensor cores -------------------------------------------------------------------
 // C = alpha * op(A) op(B) + beta * D   (D may alias C or be null); opA/opB: 0 = as is, 1 = transposed.
 // C must not alias A or B.
-__device__ __noinline__ void la_gemm(double* C, const double* A, int tA, const double* B,
+static __device__ __noinline__ void la_gemm(double* C, const double* A, int tA, const double* B,
                                int tB, int T, double alpha, double beta, const double* D, LaSmem& sm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
@@ -147,7 +147,7 @@ __device__ __noinline__ void la_gemm(double* C, const double* A, int tA, const d
 
 // ---- Cholesky (lower, in place; strict upper part zeroed) ---------------------------------------------
 // returns 0 or (index + 1) of the first non-positive pivot
-__device__ __noinline__ int la_chol(double* A, int T, LaSmem& sm) {
+static __device__ __noinline__ int la_chol(double* A, int T, LaSmem& sm) {
     const int tid = threadIdx.x;
     if (tid == 0) sm.flag = 0;
     for (int i = tid; i < T * T; i += LA_THREADS) if (i % T > i / T) A[i] = 0.0;
@@ -224,7 +224,7 @@ __device__ __noinline__ int la_chol(double* A, int T, LaSmem& sm) {
 
 // ---- triangular solves with T right-hand sides (in place on B) --------------------------------------
 // B <- L^{-1} B  (forward substitution), L lower triangular
-__device__ __noinline__ void la_trsm_lower(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
+static __device__ __noinline__ void la_trsm_lower(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
     const int tid = threadIdx.x;
     for (int r0 = 0; r0 < T; r0 += LA_NB) {
         const int nb = min(LA_NB, T - r0);
@@ -255,7 +255,7 @@ __device__ __noinline__ void la_trsm_lower(const double* __restrict__ L, double*
     }
 }
 // B <- L^{-T} B  (backward substitution with the transpose of a lower-triangular L)
-__device__ __noinline__ void la_trsm_lower_trans(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
+static __device__ __noinline__ void la_trsm_lower_trans(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
     const int tid = threadIdx.x;
     const int nblk = (T + LA_NB - 1) / LA_NB;
     for (int b = nblk - 1; b >= 0; --b) {
@@ -289,7 +289,7 @@ __device__ __noinline__ void la_trsm_lower_trans(const double* __restrict__ L, d
 // ---- LU with partial pivoting (in place) and solve with T right-hand sides -----------------------------
 // piv[k] = row swapped with k at step k (global memory, T ints).  Unblocked column loop with the trailing
 // update spread over the CTA: 2/3 T^3 flops, the matrix stays in L2.
-__device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaSmem& sm) {
+static __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaSmem& sm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = 0; k < T; ++k) {
         // pivot search in column k, rows k..T-1 (first maximum of |a|, like LAPACK idamax)
@@ -337,7 +337,7 @@ __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaSmem& sm
     }
 }
 // B <- A^{-1} B using the factorization above (B: T x T, in place)
-__device__ __noinline__ void la_lu_solve(const double* __restrict__ LU, const int* __restrict__ piv, double* B, int T, LaSmem& sm) {
+static __device__ __noinline__ void la_lu_solve(const double* __restrict__ LU, const int* __restrict__ piv, double* B, int T, LaSmem& sm) {
     const int tid = threadIdx.x;
     for (int k = 0; k < T; ++k) {   // apply the row interchanges
         const int p = piv[k];

@@ -333,3 +333,19 @@ def mniw_loglik_batched(M, M_idx, Sigma, S_idx, prior_mean, pm_idx, prior_rcov, 
                                       ptr(mats[3]), ptr(idx[3]), ptr(mats[4]), ptr(idx[4]), J, T, ptr(out), ptr(info),
                                       ptr(ws), need, stream_ptr()), "hgp_mniw_loglik_batched")
     return out, info
+
+
+def hyperfit_batched(x, Y, noise_bounds, lr=0.1, max_iter=4000, min_iter=1000, atol=1e-4):
+    """IterativeGaussianProcess.fit_torch's optimisation (GPI.py:610-698) for every row of Y [n_fits, T] at once.
+    Returns a float64 CUDA tensor [n_fits, 8]: outputscale, lengthscale, noise, constant mean, last loss, iterations,
+    Cholesky info, 0."""
+    lib = _lib_ready()
+    x = _dev(x).to(F64).contiguous().reshape(-1)
+    Y = _dev(Y).to(F64).contiguous().reshape(-1, x.numel())
+    n, T = Y.shape
+    out = torch.zeros((n, 8), dtype=F64, device=Y.device)
+    work = torch.empty(int(lib.hgp_hyperfit_work_doubles(n, T)), dtype=F64, device=Y.device)
+    check(lib.hgp_hyperfit_batched(ptr(x), ptr(Y), n, T, float(noise_bounds[0]), float(noise_bounds[1]), float(lr),
+                                   int(max_iter), int(min_iter), float(atol), ptr(out), ptr(work), stream_ptr()),
+          "hgp_hyperfit_batched")
+    return out

@@ -191,6 +191,17 @@ int hgp_pred_dist_inducing(const double* x_basis, int nb, const double* x_post, 
                            int64_t n_items, double kernel_const, double kernel_length, double kernel_noise,
                            double* f_out, double* cov_out, double* work, int* info, void* stream);
 
+/* ---- one-beat GP hyper-parameter fit, batched over beats: IterativeGaussianProcess.fit_torch (GPI.py:610-770,
+ *      ExactGPModel branch: x_train == x_basis) with the gpytorch ExactGP objective restated in closed form
+ *      (ConstantMean, ScaleKernel(RBF), GaussianLikelihood with Interval(noise_lo, noise_hi); Adam(lr) on -MLL / T;
+ *      at most max_iter iterations, stop once more than min_iter losses exist and the last ten loss differences sum
+ *      to within atol of zero, GPI.py:695-698).  One persistent CTA per fit.
+ * x [T]; Y [n_fits][T]; out [n_fits][8] = outputscale, lengthscale, noise, constant mean, last loss, iterations,
+ * Cholesky info (0 = ok), 0.  work: hgp_hyperfit_work_doubles(n_fits, T) doubles. */
+int64_t hgp_hyperfit_work_doubles(int n_fits, int T);
+int hgp_hyperfit_batched(const double* x, const double* Y, int n_fits, int T, double noise_lo, double noise_hi, double lr,
+                         int max_iter, int min_iter, double atol, double* out, double* work, void* stream);
+
 /* ---- MNIW log-likelihood of LDS parameters under the prior: matrix_normal_inv_wishart.log_likelihood_MNIW
  *      (GPI_model.py:1346-1362), the per-cluster ELBO term of return_LDS_param_likelihood (:459-486) ----
  * For j in [0, J):  L = chol(sym(Sigma[S_idx[j]]) + 1e-8 I);  D = M[M_idx[j]] - prior_mean[pm_idx[j]]

@@ -375,6 +375,32 @@ def test_mniw_loglik_vs_oracle(T):
     assert int(torch.count_nonzero(info)) == 0 and rel(out, want) < TOL
 
 
+def test_hyperfit_vs_oracle(golden):
+    """One-beat GP hyper-fit (parity unpinned against gpytorch, see oracle/hyperfit.py): the device
+    optimiser (closed-form MLL gradient, Adam, stop rule) against the autograd restatement, batched over beats, on
+    MIT-BIH beats at the shipped shape (T=90) and on a short synthetic grid; then the fitted chain prior."""
+    from hdpgpc_b200 import ops
+    from oracle import hyperfit
+    z = golden("offline_rec100_T90_L1")
+    Y = z["data"][:3, :, 0]
+    x = z["x_basis"].reshape(-1)
+    nb = z["kernel_def_noise_bounds"]
+    out = ops.hyperfit_batched(cu(x), cu(Y), nb).cpu().numpy()
+    for k in range(Y.shape[0]):
+        s, ell, noise, n_it = hyperfit.fit_exact_gp(torch.from_numpy(x), torch.from_numpy(Y[k]), nb)
+        assert int(out[k, 5]) == n_it and int(out[k, 6]) == 0
+        assert abs(out[k, 0] - s) < 1e-6 * s and abs(out[k, 1] - ell) < 1e-6 * ell and abs(out[k, 2] - noise) < 1e-6 * noise
+    # a short run (no early stop) pins the trajectory itself at tight tolerance
+    rng = np.random.default_rng(5)
+    xs = np.arange(24.0)
+    Ys = 40.0 * np.sin(xs[None, :] / 3.0 + rng.uniform(0, 3, size=(4, 1))) + rng.normal(size=(4, 24))
+    out = ops.hyperfit_batched(cu(xs), cu(Ys), (0.5, 30.0), max_iter=60, min_iter=1000).cpu().numpy()
+    for k in range(4):
+        s, ell, noise, n_it = hyperfit.fit_exact_gp(torch.from_numpy(xs), torch.from_numpy(Ys[k]), (0.5, 30.0), training_iter=60)
+        assert n_it == 60 == int(out[k, 5])
+        assert abs(out[k, 0] - s) < TOL * s and abs(out[k, 1] - ell) < TOL * ell and abs(out[k, 2] - noise) < TOL * noise
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
