@@ -42,6 +42,7 @@ PROTOTYPES = {
     "hgp_emission_means": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
     "hgp_warp_fit_batched": (_int, [_p, _int, _p, _i64, _p, _int, _p, _int, _int, _dbl, _dbl, _dbl, _dbl, _p, _p, _p, _p,
                                     _p, _p]),
+    "hgp_rbf_kernel_matrix": (_int, [_p, _int, _p, _int, _dbl, _dbl, _dbl, _p, _p]),
     "hgp_hyperfit_work_doubles": (_i64, [_int, _int]),
     "hgp_hyperfit_batched": (_int, [_p, _p, _int, _int, _dbl, _dbl, _dbl, _int, _int, _dbl, _p, _p, _p]),
     "hgp_mniw_workspace_bytes": (_i64, [_i64, _int]),

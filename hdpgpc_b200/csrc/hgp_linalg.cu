@@ -291,3 +291,27 @@ extern "C" int hgp_pack_factors(const double* W, int64_t F, int T, double* Wpack
     HGP_LAUNCH_CHECK("hgp_pack_factors");
     return 0;
 }
+
+// ---- kernel matrix of ConstantKernel(c) * RBF(l) (+ WhiteKernel on the diagonal when asked) -----------------------
+// sklearn evaluates exp(-0.5 * sqeuclidean(x / l, y / l)) (reference call sites GPI_model.py:50,228; GPI.py:124-139);
+// the division happens before the difference, and so it does here.
+namespace {
+__global__ void rbf_kernel_matrix_kernel(const double* __restrict__ xa, int na, const double* __restrict__ xb, int nb,
+                                         double c, double ell, double diag_add, double* __restrict__ K) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= na * nb) return;
+    const int i = idx / nb, j = idx % nb;
+    const double d = xa[i] / ell - xb[j] / ell;
+    K[idx] = c * exp(-0.5 * (d * d)) + ((i == j) ? diag_add : 0.0);
+}
+}  // namespace
+
+extern "C" int hgp_rbf_kernel_matrix(const double* xa, int na, const double* xb, int nb, double kernel_const,
+                                     double kernel_length, double diag_add, double* K, void* stream) {
+    HGP_REQUIRE(na > 0 && nb > 0 && (int64_t)na * nb < (1ll << 31), "hgp_rbf_kernel_matrix: bad sizes");
+    const int n = na * nb;
+    rbf_kernel_matrix_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(xa, na, xb, nb, kernel_const, kernel_length,
+                                                                              diag_add, K);
+    HGP_LAUNCH_CHECK("hgp_rbf_kernel_matrix");
+    return 0;
+}

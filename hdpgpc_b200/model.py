@@ -438,30 +438,62 @@ class GPI_model:
         fitted kernel (const, length, noise) of ConstantKernel*RBF + WhiteKernel."""
         x = np.asarray(x_basis, dtype=np.float64).reshape(-1)
         T = x.shape[0]
-        c, ell, noise = (float(v) for v in kernel)
-        d = (x[:, None] / ell - x[None, :] / ell) ** 2
-        K = c * np.exp(-0.5 * d)
         I = np.eye(T)
         self = cls(x, [np.zeros(T)], [np.zeros(T)], [I], [ini_sigma * I], [], estimation_limit=estimation_limit,
-                   A=[I], Gamma=[ini_gamma * I], cov_f_sm=[K], device=device)
-        self.cov_f = _stack([K], self.device)
-        self.kernel = (c, ell, noise)
-        self.ini_cov_is_prior = True
+                   A=[I], Gamma=[ini_gamma * I], cov_f_sm=[I], device=device)
         self.free_deg = float(free_deg)
         self.annealing = annealing
-        self.fitted = True
+        self._set_kernel(kernel)
         return self
+
+    @classmethod
+    def unfitted(cls, x_basis, noise_bounds, ini_sigma, ini_gamma, free_deg=5, estimation_limit=None, annealing=True,
+                 device="cuda"):
+        """A default model whose kernel is still to be fitted: full_pass_weighted runs the one-beat hyper-fit on its
+        first member (GPI_model.include_weighted_sample :353-375 -> fit_kernel_params :207-241 -> fit_torch)."""
+        self = cls.fresh(x_basis, (1.0, 1.2, float(noise_bounds[0])), ini_sigma, ini_gamma, free_deg, estimation_limit,
+                         annealing, device)
+        self.fitted = False
+        self.noise_bounds = (float(noise_bounds[0]), float(noise_bounds[1]))
+        return self
+
+    def _set_kernel(self, kernel):
+        """fit_kernel_params' side effects (:228-231): prior covariance = kernel(x_basis, x_basis) without the white part."""
+        c, ell, noise = (float(v) for v in kernel)
+        self.kernel = (c, ell, noise)
+        xb = torch.from_numpy(self.x_basis).to(self.device)
+        K = ops.rbf_kernel_matrix(xb, xb, c, ell)
+        self.cov_f = K[None].clone()
+        self.cov_f_sm = K[None].clone()
+        self.ini_cov_is_prior = True
+        self.fitted = True
+        self._tables = None
+
+    def fit_kernel_params(self, x_train, y):
+        """GPI_model.fit_kernel_params (:207-241): hyper-fit on one beat (device, see csrc/hgp_hyperfit.cu); keeps the
+        fitted outputscale and noise, sets the RBF lengthscale to 1.2 (GPI.py:711)."""
+        if self._off_grid(x_train) is not None:
+            raise HgpError("fit_kernel_params on a grid other than x_basis (ProjectedGPModel branch) is not built")
+        Y = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
+                                                   dtype=np.float64).reshape(1, -1)))
+        out = ops.hyperfit_batched(torch.from_numpy(self.x_basis).to(self.device), Y, self.noise_bounds)[0].cpu().numpy()
+        if int(out[6]):
+            raise LinAlgError("hyper-fit: kernel matrix lost positive-definiteness")
+        self.hyperfit_iterations = int(out[5])
+        self._set_kernel((out[0], 1.2, out[2]))
+        return self.kernel
 
     def _chain_prepare(self, Y, resp):
         """Allocate the histories of a fresh chain and fill its hgp_chain_desc (None if no member)."""
-        if self.N != 0 or not getattr(self, "fitted", False):
-            raise HgpError("device full_pass_weighted needs a fresh fitted model (GPI_model.fresh); the hyper-fit "
-                           "(GPI.py:610-770) is not built on the device yet")
+        if self.N != 0 or not hasattr(self, "fitted"):
+            raise HgpError("device full_pass_weighted replays a chain from an empty model (GPI_model.fresh / unfitted)")
         r = resp if isinstance(resp, torch.Tensor) else torch.from_numpy(np.asarray(resp, dtype=np.float64))
         active = torch.nonzero(r.to(self.device) > 0.99).flatten()
         n = int(active.numel())
         if n == 0:
             return None
+        if not self.fitted:
+            self.fit_kernel_params(None, Y[int(active[0])])
         T, dev = self.T, self.device
         z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
         hist = {k: z(n + 1, T, T) for k in ("cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma")}

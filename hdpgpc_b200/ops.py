@@ -349,3 +349,14 @@ def hyperfit_batched(x, Y, noise_bounds, lr=0.1, max_iter=4000, min_iter=1000, a
                                    int(max_iter), int(min_iter), float(atol), ptr(out), ptr(work), stream_ptr()),
           "hgp_hyperfit_batched")
     return out
+
+
+def rbf_kernel_matrix(xa, xb, const, length, diag_add=0.0):
+    """ConstantKernel(const) * RBF(length) between two 1-D grids, sklearn's evaluation order; [na, nb] CUDA tensor."""
+    lib = _lib_ready()
+    xa = _dev(xa).to(F64).contiguous().reshape(-1)
+    xb = _dev(xb).to(F64).contiguous().reshape(-1)
+    K = torch.empty((xa.numel(), xb.numel()), dtype=F64, device=xa.device)
+    check(lib.hgp_rbf_kernel_matrix(ptr(xa), xa.numel(), ptr(xb), xb.numel(), float(const), float(length),
+                                    float(diag_add), ptr(K), stream_ptr()), "hgp_rbf_kernel_matrix")
+    return K

@@ -191,6 +191,12 @@ int hgp_pred_dist_inducing(const double* x_basis, int nb, const double* x_post, 
                            int64_t n_items, double kernel_const, double kernel_length, double kernel_noise,
                            double* f_out, double* cov_out, double* work, int* info, void* stream);
 
+/* ---- kernel matrix K[i][j] = c exp(-0.5 (xa_i / l - xb_j / l)^2) + diag_add [i == j]: sklearn's
+ *      ConstantKernel * RBF (+ WhiteKernel) as the reference evaluates it for the GP prior of a fresh cluster
+ *      (GPI_model.py:50, :228-231) and inside the Kalman update (GPI.py:124-139). */
+int hgp_rbf_kernel_matrix(const double* xa, int na, const double* xb, int nb, double kernel_const, double kernel_length,
+                          double diag_add, double* K, void* stream);
+
 /* ---- one-beat GP hyper-parameter fit, batched over beats: IterativeGaussianProcess.fit_torch (GPI.py:610-770,
  *      ExactGPModel branch: x_train == x_basis) with the gpytorch ExactGP objective restated in closed form
  *      (ConstantMean, ScaleKernel(RBF), GaussianLikelihood with Interval(noise_lo, noise_hi); Adam(lr) on -MLL / T;

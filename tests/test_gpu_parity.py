@@ -208,6 +208,21 @@ def test_chain_replay_vs_reference(golden, name):
                 assert np.max(np.abs(mine[-1] - ref)) < 1e-8 * np.max(np.abs(ref))
 
 
+def test_chain_replay_with_device_hyperfit(golden):
+    """The whole fresh-cluster path on the device: hyper-fit on the first member (a10), prior from the fitted kernel,
+    chain replay (a5-a9), scores (a1, a4) -- against the reference run (whose hyper-fit is the autograd restatement)."""
+    import hdpgpc_b200 as hb
+    z = golden("offline_rec100_T30_L1")
+    Y = z["data"]
+    pre = "chain_0_"
+    gp = hb.GPI_model.unfitted(z["x_basis"], z["kernel_def_noise_bounds"], float(z["ini_sigma_def"]),
+                               float(z["ini_gamma_def"]), free_deg=float(z["free_deg_MNIV"]))
+    q, ql = gp.full_pass_weighted(None, Y[:, :, [0]], z[pre + "resp"])
+    k_ref = z[pre + "kernel"]
+    assert abs(gp.kernel[0] - k_ref[0]) < 1e-6 * k_ref[0] and gp.kernel[1] == 1.2 and abs(gp.kernel[2] - k_ref[2]) < 1e-6 * k_ref[2]
+    assert rel(q, z[pre + "q"]) < 1e-5 and rel(ql, z[pre + "q_lat"]) < 1e-5
+
+
 def test_online_extras_vs_reference(golden):
     """estimate_new -> smoother_weighted -> posterior_weighted -> log_sq_error(mean, cov, C, Sigma) on the device."""
     import hdpgpc_b200 as hb
