@@ -205,7 +205,7 @@ def run_ours(args):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.score_tiles(tb.Y, tb.mu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[ld])
+            ops.score_tiles(tb.Y, tb.nu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[ld], tile_state=tb.tile_state)
             if record:
                 e1.record()
                 tile_events.append((e0, e1))

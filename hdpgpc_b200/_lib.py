@@ -21,7 +21,10 @@ PROTOTYPES = {
     "hgp_tri_inverse_batched": (_int, [_p, _i64, _int, _p, _p]),
     "hgp_packed_factor_bytes": (_i64, [_int]),
     "hgp_pack_factors": (_int, [_p, _i64, _int, _p, _p]),
-    "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p]),
+    "hgp_tile_beats": (_int, []),
+    "hgp_tile_uniform_states": (_int, [_p, _i64, _int, _p, _p]),
+    "hgp_whiten_means": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
+    "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p]),
     "hgp_score_pairs": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _i64, _p, _p]),
     "hgp_snr_states": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p]),
     "hgp_lead_weights": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p]),

@@ -2,17 +2,24 @@
 // log_sq_error :250-286; _gaussian_score_shared_cov :92-113) and the SNR lead statistic
 // (GPI_HDP.compute_snr, GPI_HDP.py:732-748), hand-written for sm_100a.
 //
-// score_tiles_kernel -- the hot kernel.  For a tile of 64 consecutive beats and a run of clusters it
-// evaluates  z = W_m (y_n - mu_{s(n,m)})  as a lower-triangular matrix product on the FP64 tensor
-// cores (DMMA.8x8x4) and reduces |z|^2 per beat in the epilogue.  Warp-specialised:
-//   * producer warpgroup (4 warps, registers released with setmaxnreg.dec): streams W_m in
-//     fragment-ordered k-chunks with 1-D bulk async copies (TMA, completion on an mbarrier) through a
-//     4-stage shared-memory ring, and builds the matching 8 x 64 slice of D = Y - mu (beat tile
-//     resident in shared memory, means gathered through L2) directly in B-fragment order;
-//   * 2 consumer warpgroups (8 warps, setmaxnreg.inc): row blocks of 8 are dealt to warps in a mirrored
-//     order so that the triangular
-//     shrinkage (row block rb only needs k-chunks kc <= rb) stays balanced over the 4 SM
-//     sub-partitions; each warp keeps its 32 x 64 slice of z in registers (64 f64 accumulators/lane).
+// score_tiles_kernel -- the hot kernel.  For a tile of 64 consecutive beats and a run of clusters it evaluates
+//     z = W_m y_n - nu_{s(n,m)},   nu_s = W_m mu_s  (whitened state means, hgp_whiten_means),   q = -|z|^2/2 - T log(2 pi)/2
+// as a lower-triangular matrix product on the FP64 tensor cores (DMMA.8x8x4) with the mean subtracted in the
+// epilogue.  Why not z = W (y - mu): building D = Y - mu per (tile, cluster) needs 16384 scalar FP64 subtractions per
+// item, and scalar FP64 instructions share the pipe with DMMA -- each one queues ~150 cycles behind the tensor
+// stream and the producer warps fell behind (measured: 13 % of the kernel).  With the product taken on y alone the
+// B operand is the SAME for every cluster, so the beat tile is stored once per item directly in B-fragment order
+// and nothing but the factors W_m moves through the pipeline; the subtraction shrinks to 64 per lane per item
+// against a per-item vector nu (all beats of a tile almost always score against the same state of a cluster,
+// hgp_tile_uniform_states) or, for the few (tile, cluster) items that contain members of the cluster, a gathered
+// nu row per beat.  |W y| is 1e2-1e3 times |z|, so the cancellation costs ~3 of the 16 digits: q agrees with the
+// reference's cholesky_solve form to ~1e-13 relative (tests: 1e-8 required).
+//   * producer warpgroup: an elected thread streams W_m in fragment-ordered k-chunks with 1-D bulk async copies (TMA,
+//     completion on an mbarrier) through a 5-stage shared-memory ring; one stage carries TWO k-chunks, s and
+//     nrb-1-s, so that every stage holds the same amount of triangular work;
+//   * 8 consumer warps: row blocks of 8 are dealt to warps in a mirrored order (w, 15-w, 16+w, 31-w) so the
+//     triangular shrinkage stays balanced over the 4 SM sub-partitions; each warp keeps its 32 x 64 slice of z in
+//     registers (64 f64 accumulators per lane).
 #include "hgp_common.cuh"
 #include <type_traits>
 
@@ -53,88 +60,103 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+#ifdef HGP_NO_MMA   // experiment: everything but the tensor-core instruction (operands stay live)
+__device__ __forceinline__ void tile_mma(double& c0, double& c1, double a, double b) { asm volatile("" ::"d"(a), "d"(b), "d"(c0), "d"(c1)); }
+#else
+__device__ __forceinline__ void tile_mma(double& c0, double& c1, double a, double b) { dmma884(c0, c1, a, b); }
+#endif
+
 constexpr int BT = 64;            // beats per tile
-constexpr int NCW = 8;            // consumer warps (warpgroups 0 and 1)
-constexpr int NPW = 4;            // producer warps (warpgroup 2)
-constexpr int STAGES = 4;
+constexpr int NCW = 8;            // consumer warps
+constexpr int NPW = 4;            // producer warpgroup: one elected thread issues the bulk copies; the other warps only hold
+                                  // registers for the consumers (a sub-partition's registers are shared by ITS warps: a
+                                  // CTA of 9 warps would cap everyone at 168, the donors let the consumers have 232)
+#define HGP_CONSUMER_REGS 232
+#define HGP_PRODUCER_REGS 40
+constexpr int STAGES = 5;
 constexpr int MAX_NRB = 32;       // T <= 256
 constexpr int TILE_THREADS = (NCW + NPW) * 32;
-constexpr int W_STAGE_BYTES = MAX_NRB * 512;   // 16 KB
-constexpr int D_STAGE_BYTES = 8 * BT * 8;      // 4 KB
-// Register re-balancing between the warpgroups (setmaxnreg): the kernel launches with 168
-// registers/thread (3 warps per SM sub-partition); consumers grow, producers shrink.
-// Per sub-partition: 2 consumer warps x 32 x 216 + 1 producer warp x 32 x 72 = 16128 <= 16384.
-#ifndef HGP_PF
-#define HGP_PF 2
-#endif
-constexpr int PF = HGP_PF;     // producer prefetch depth (k-chunks of gathered means in flight)
-#define HGP_CONSUMER_REGS 216
-#define HGP_PRODUCER_REGS 72
-
-__device__ __forceinline__ int chunk_of(int i, int nrb) { (void)nrb; return i; }   // k-chunks in ascending order
-
+// One pipeline step carries TWO k-chunks, s and nrb-1-s: the triangular product needs nrb-kc row blocks of chunk kc,
+// so the pair always adds up to nrb+1 blocks -- every step has the same tensor-core work and the same stage size,
+// instead of steps that shrink to one row block at the end of the k-loop while the per-step cost stays the same.
+constexpr int W_STAGE_BYTES = (MAX_NRB + 1) * 512;   // 16.5 KB
+constexpr int Y_CHUNK_DOUBLES = 8 * BT;              // one 8 x 64 slice of the beat tile in B-fragment order (4 KB)
 
 struct TileSmem {
     // offsets (bytes) into dynamic shared memory
-    int ytile, wst, dst, red, bars, total;
+    int ytile, wst, red, bars, total;
 };
-__host__ __device__ inline TileSmem tile_smem_layout(int Tp) {
+__host__ __device__ inline TileSmem tile_smem_layout(int nrb) {
     TileSmem s;
-    int yp = Tp + 2;
     s.ytile = 0;
-    s.wst = ((BT * yp * 8) + 127) / 128 * 128;
-    s.dst = s.wst + STAGES * W_STAGE_BYTES;
-    s.red = s.dst + STAGES * D_STAGE_BYTES;
-    s.bars = s.red + 2 * NCW * BT * 8;
+    s.wst = nrb * Y_CHUNK_DOUBLES * 8;
+    s.red = s.wst + STAGES * W_STAGE_BYTES;
+    s.bars = s.red + 2 * NCW * BT * 8 + BT * 4;      // + the tile's state indices (mixed-state epilogue)
     s.total = s.bars + 2 * STAGES * 8;
     return s;
 }
 
-// Beat tile -> shared memory, zero padded (rows n >= N, samples t >= T), by all warps of the CTA.
-__device__ __forceinline__ void load_beat_tile(double* Ytile, const double* __restrict__ Y, int64_t N, int T, int YP,
+// Beat tile -> shared memory in B-fragment order, zero padded (rows n >= N, samples t >= T), by all warps of the CTA.
+// Sample t of beat c goes to chunk t/8, double2 slot (c/8)*32 + (c%8)*4 + t%4, component (t%8)/4: the lane that owns
+// column c%8 and k-index t%4 of n-tile c/8 finds both of its k-steps in one 16-byte load.
+__device__ __forceinline__ void load_beat_tile(double* Yfrag, const double* __restrict__ Y, int64_t N, int T, int nrb,
                                                int64_t n0, int warp, int lane) {
-    const bool vec = ((T & 1) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
     for (int c = warp; c < BT; c += NCW + NPW) {
         const int64_t n = n0 + c;
-        double* dst = Ytile + c * YP;
-        if (n < N && vec) {
-            const double2* src = reinterpret_cast<const double2*>(Y + n * T);
-            for (int t2 = lane; t2 < YP / 2; t2 += 32)
-                reinterpret_cast<double2*>(dst)[t2] = (2 * t2 < T) ? src[t2] : make_double2(0.0, 0.0);
-        } else {
-            const double* src = Y + n * T;
-            for (int t = lane; t < YP; t += 32) dst[t] = (n < N && t < T) ? src[t] : 0.0;
-        }
+        const double* src = Y + n * T;
+        double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
+        for (int t = lane; t < nrb * 8; t += 32)
+            base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = (n < N && t < T) ? __ldg(src + t) : 0.0;
     }
 }
 
-// One k-chunk for a warp whose row blocks j >= J0 are active (T = 256 fast path): no per-block tests,
-// so the A/B fragment loads of the whole chunk are issued up front and the 16 * (4 - J0) tensor-core
-// instructions follow as one straight-line stream.
-template <int J0>
-__device__ __forceinline__ void fast_chunk(double (&acc)[4][8][2], uint32_t it, int kc, int rb0, int rb1, int rb2,
-                                           int rb3, int lane, const unsigned char* Wst, const unsigned char* Dst,
-                                           uint64_t* full_bar, uint64_t* empty_bar) {
-    const int stage = it & (STAGES - 1);
-    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
-    if (J0 < 4) {
-        const double2* ds = reinterpret_cast<const double2*>(Dst + stage * D_STAGE_BYTES) + lane;
-        const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane - kc * 32;
-        double2 b[8];
+// One pipeline step (k-chunks s and 31-s) of the T = 256 fast path for a warp whose row blocks j >= JA are active in
+// chunk s and j >= JB in chunk 31-s: no per-block tests, the fragment loads are issued up front and the tensor-core
+// instructions follow as one straight-line stream (64 to 80 DMMAs per step).
+template <int JA, int JB>
+__device__ __forceinline__ void fast_step(double (&acc)[4][8][2], uint32_t it, int s, int rb0, int rb1, int rb2,
+                                          int rb3, int lane, const unsigned char* Wst, const double* Yfrag,
+                                          uint64_t* full_bar, uint64_t* empty_bar) {
+    const int stage = it % STAGES;
+    const double2* ya = reinterpret_cast<const double2*>(Yfrag + s * Y_CHUNK_DOUBLES) + lane;
+    double2 b[8];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) b[nt] = ds[nt * 32];
+    for (int nt = 0; nt < 8; ++nt) b[nt] = ya[nt * 32];      // the beat fragments do not depend on the pipeline
+    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+    const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane;
+    {
+        // chunk s: block rb sits at (rb - s) * 512 bytes
+        const double2* wa = ws - s * 32;
         double2 a[4];
-        if (J0 <= 0) a[0] = ws[rb0 * 32];
-        if (J0 <= 1) a[1] = ws[rb1 * 32];
-        if (J0 <= 2) a[2] = ws[rb2 * 32];
-        if (J0 <= 3) a[3] = ws[rb3 * 32];
+        if (JA <= 0) a[0] = wa[rb0 * 32];
+        if (JA <= 1) a[1] = wa[rb1 * 32];
+        if (JA <= 2) a[2] = wa[rb2 * 32];
+        if (JA <= 3) a[3] = wa[rb3 * 32];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j >= J0) {
+            if (j >= JA) {
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a[j].x, b[nt].x);
+                for (int nt = 0; nt < 8; ++nt) tile_mma(acc[j][nt][0], acc[j][nt][1], a[j].x, b[nt].x);
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a[j].y, b[nt].y);
+                for (int nt = 0; nt < 8; ++nt) tile_mma(acc[j][nt][0], acc[j][nt][1], a[j].y, b[nt].y);
+            }
+        }
+    }
+    if (JB < 4) {
+        // chunk 31 - s follows the 32 - s blocks of chunk s: block rb sits at (32 - s + rb - (31 - s)) = (rb + 1) * 512
+        const double2* yb = reinterpret_cast<const double2*>(Yfrag + (MAX_NRB - 1 - s) * Y_CHUNK_DOUBLES) + lane;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) b[nt] = yb[nt * 32];
+        double2 a[4];
+        if (JB <= 2) a[2] = ws[(rb2 + 1) * 32];
+        if (JB <= 3) a[3] = ws[(rb3 + 1) * 32];
+#pragma unroll
+        for (int j = 2; j < 4; ++j) {
+            if (j >= JB) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) tile_mma(acc[j][nt][0], acc[j][nt][1], a[j].x, b[nt].x);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) tile_mma(acc[j][nt][0], acc[j][nt][1], a[j].y, b[nt].y);
             }
         }
     }
@@ -143,19 +165,15 @@ __device__ __forceinline__ void fast_chunk(double (&acc)[4][8][2], uint32_t it, 
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 1)
-score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu,
+score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ nu,
                    const double* __restrict__ Wpacked, int64_t packed_doubles, const int* __restrict__ state_of,
-                   const int* __restrict__ factor_of_cluster, int M, int m_per_item, int m_splits, int64_t n_items,
-                   double* __restrict__ q, const double* __restrict__ mu_sm, const int* __restrict__ snr_state_of,
-                   double* __restrict__ snr) {
+                   const int* __restrict__ tile_state, const int* __restrict__ factor_of_cluster, int M, int m_per_item,
+                   int m_splits, int64_t n_items, double* __restrict__ q) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nrb = (T + 7) / 8;
-    const int Tp = nrb * 8;
-    const int YP = Tp + 2;
-    const TileSmem lay = tile_smem_layout(Tp);
-    double* Ytile = reinterpret_cast<double*>(smem_raw + lay.ytile);
+    const TileSmem lay = tile_smem_layout(nrb);
+    double* Yfrag = reinterpret_cast<double*>(smem_raw + lay.ytile);
     unsigned char* Wst = smem_raw + lay.wst;
-    unsigned char* Dst = smem_raw + lay.dst;
     double* red = reinterpret_cast<double*>(smem_raw + lay.red);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -167,101 +185,44 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1 + NPW);   // arrive.expect_tx (W bytes) + one arrive per producer warp (D part)
+            mbar_init(&full_bar[s], 1);         // the producer's arrive.expect_tx; the bulk copies complete the bytes
             mbar_init(&empty_bar[s], NCW);      // one arrive per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    uint32_t it = 0;   // running (m, kc) step counter; identical in producers and consumers
+    uint32_t it = 0;   // running pipeline-step counter; identical in producer and consumers
     const double half_T_log2pi = 0.5 * (double)T * HGP_LOG2PI;
+    const int n_steps = (nrb + 1) >> 1;
 
     if (warp >= NCW) {
-        // ===================================== producers =====================================
+        // ===================================== producer =====================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HGP_PRODUCER_REGS));
-        const int pw = warp - NCW;            // this warp builds n-tiles 2*pw and 2*pw+1 of every D chunk
-        const int kk = lane & 3, nn = lane >> 2;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int64_t tile = item / m_splits;
             const int m_begin = (int)(item % m_splits) * m_per_item;
             const int m_end = min(M, m_begin + m_per_item);
-            const int64_t n0 = tile * BT;
-            load_beat_tile(Ytile, Y, N, T, YP, n0, warp, lane);
-            __syncthreads();   // tile complete (all 12 warps load it)
-            const double* y0 = Ytile + ((2 * pw) * 8 + nn) * YP + kk;
-            const double* y1 = y0 + 8 * YP;
-            // State indices are fetched two clusters ahead and the mean rows of cluster m+1 are pulled into L2
-            // while cluster m is produced: the per-chunk gathers below then hit L2 instead of HBM.
-            const int64_t na = n0 + (2 * pw) * 8 + nn, nb = na + 8;
-            auto load_state = [&](int m, int& sa, int& sb) {
-                sa = (m < m_end && na < N) ? state_of[na * M + m] : -1;
-                sb = (m < m_end && nb < N) ? state_of[nb * M + m] : -1;
-            };
-            auto prefetch_rows = [&](int sa, int sb) {
-                // the 4 lanes of a column (kk = 0..3) split its row into 128-byte lines
-                const int lines = (T * 8 + 127) / 128;
-                for (int l = kk; l < lines; l += 4) {
-                    if (sa >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(mu + (int64_t)sa * T + l * 16));
-                    if (sb >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(mu + (int64_t)sb * T + l * 16));
-                }
-            };
-            int sa, sb, sa1, sb1, sa2, sb2;
-            load_state(m_begin, sa, sb);
-            load_state(m_begin + 1, sa1, sb1);
-            prefetch_rows(sa, sb);
-            for (int m = m_begin; m < m_end; ++m) {
-                const unsigned char* Wp =
-                    reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
-                load_state(m + 2, sa2, sb2);
-                prefetch_rows(sa1, sb1);
-                const double* ma = (sa >= 0) ? mu + (int64_t)sa * T + kk : nullptr;
-                const double* mb = (sb >= 0) ? mu + (int64_t)sb * T + kk : nullptr;
-                // The means are gathered through L2 (~650 cycles): keep PF chunks of them in flight in a
-                // register ring so the producer never waits on a load it issued less than PF steps ago.
-                double ring[PF][4];
-                auto load_chunk = [&](int i, double (&dst)[4]) {
-                    dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
-                    if (i < nrb) {
-                        const int o = 8 * chunk_of(i, nrb);
-                        const bool w0 = o + kk < T, w1 = o + kk + 4 < T;
-                        if (ma) { if (w0) dst[0] = __ldg(ma + o); if (w1) dst[1] = __ldg(ma + o + 4); }
-                        if (mb) { if (w0) dst[2] = __ldg(mb + o); if (w1) dst[3] = __ldg(mb + o + 4); }
-                    }
-                };
-#pragma unroll
-                for (int p = 0; p < PF; ++p) load_chunk(p, ring[p]);
-                for (int i0 = 0; i0 < nrb; i0 += PF) {
-#pragma unroll
-                    for (int p = 0; p < PF; ++p) {
-                        const int i = i0 + p;
-                        if (i < nrb) {
-                            const int kc = chunk_of(i, nrb);
-                            const int stage = it % STAGES;
-                            const uint32_t phase = (it / STAGES) & 1;
-                            const uint32_t bytes = (uint32_t)(nrb - kc) * 512u;
-                            const uint32_t off = 512u * (uint32_t)(kc * nrb - (kc * (kc - 1)) / 2);
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            if (pw == 0 && lane == 0) {
-                                mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                                bulk_g2s(Wst + stage * W_STAGE_BYTES, Wp + off, bytes, &full_bar[stage]);
-                            }
-                            double2* dstage = reinterpret_cast<double2*>(Dst + stage * D_STAGE_BYTES) + (2 * pw) * 32 + lane;
-                            double2 va, vb;   // rows t >= T: y = 0 and mu = 0
-                            va.x = ma ? y0[kc * 8] - ring[p][0] : 0.0;
-                            va.y = ma ? y0[kc * 8 + 4] - ring[p][1] : 0.0;
-                            vb.x = mb ? y1[kc * 8] - ring[p][2] : 0.0;
-                            vb.y = mb ? y1[kc * 8 + 4] - ring[p][3] : 0.0;
-                            dstage[0] = va;
-                            dstage[32] = vb;
-                            load_chunk(i + PF, ring[p]);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&full_bar[stage]);
-                            ++it;
-                        }
+            load_beat_tile(Yfrag, Y, N, T, nrb, tile * BT, warp, lane);
+            __syncthreads();   // tile complete (all warps load it)
+            if (warp == NCW && lane == 0) {
+                for (int m = m_begin; m < m_end; ++m) {
+                    const unsigned char* Wp =
+                        reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
+                    for (int st = 0; st < n_steps; ++st, ++it) {
+                        const int ka = st, kb = nrb - 1 - st;
+                        const bool two = kb > ka;
+                        const int stage = it % STAGES;
+                        const uint32_t bytes_a = (uint32_t)(nrb - ka) * 512u;
+                        const uint32_t bytes_b = two ? (uint32_t)(nrb - kb) * 512u : 0u;
+                        const uint32_t off_a = 512u * (uint32_t)(ka * nrb - (ka * (ka - 1)) / 2);
+                        const uint32_t off_b = 512u * (uint32_t)(kb * nrb - (kb * (kb - 1)) / 2);
+                        mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], bytes_a + bytes_b);
+                        bulk_g2s(Wst + stage * W_STAGE_BYTES, Wp + off_a, bytes_a, &full_bar[stage]);
+                        if (two) bulk_g2s(Wst + stage * W_STAGE_BYTES + bytes_a, Wp + off_b, bytes_b, &full_bar[stage]);
                     }
                 }
-                sa = sa1; sb = sb1; sa1 = sa2; sb1 = sb2;
             }
             __syncthreads();   // consumers are done with this item; the beat tile may be rewritten
         }
@@ -269,12 +230,14 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
         // ===================================== consumers =====================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HGP_CONSUMER_REGS));
         uint32_t epi = 0;  // running epilogue counter (double-buffers `red`)
+        const int rb_of[4] = {warp, 15 - warp, 16 + warp, 31 - warp};
+        const int qrow = lane >> 2;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int64_t tile = item / m_splits;
             const int m_begin = (int)(item % m_splits) * m_per_item;
             const int m_end = min(M, m_begin + m_per_item);
             const int64_t n0 = tile * BT;
-            load_beat_tile(Ytile, Y, N, T, YP, n0, warp, lane);
+            load_beat_tile(Yfrag, Y, N, T, nrb, n0, warp, lane);
             __syncthreads();   // tile complete
             for (int m = m_begin; m < m_end; ++m) {
                 double acc[4][8][2];
@@ -282,36 +245,53 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) acc[j][nt][0] = acc[j][nt][1] = 0.0;
-                // epilogue operand fetched early so its latency hides under the chunk loop
+                // epilogue operands fetched early so their latency hides under the k-loop:
+                // the tile's uniform state of this cluster (-1: empty cluster, -2: several states) and its nu rows
+                const int st_u = tile_state[tile * M + m];
+                double nu_r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = rb_of[j] * 8 + qrow;
+                    nu_r[j] = (st_u >= 0 && row < T) ? __ldg(nu + (int64_t)st_u * T + row) : 0.0;
+                }
                 int st_epi = -1;
                 if (tid < BT && n0 + tid < N) st_epi = state_of[(n0 + tid) * M + m];
 
                 if (nrb == MAX_NRB) {
-                    // T = 256 fast path.  This warp's row blocks rb_0 < rb_1 < rb_2 < rb_3 retire one after the
-                    // other as k advances, so the k-loop splits into phases with a FIXED active set.
+                    // T = 256 fast path.  This warp's row blocks are rb_0 = w < rb_1 = 15-w < rb_2 = 16+w < rb_3 = 31-w;
+                    // in step s (chunks s and 31-s) chunk s needs the blocks >= s and chunk 31-s the blocks >= 31-s,
+                    // which gives five phases with a FIXED active set each (4 or 5 (block, chunk) products per step).
                     const int rb0 = warp, rb1 = 15 - warp, rb2 = 16 + warp, rb3 = 31 - warp;
-                    int kc = 0;
+                    int s = 0;
 #pragma unroll 1
-                    for (; kc <= rb0; ++kc, ++it) fast_chunk<0>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+                    for (; s < rb0; ++s, ++it) fast_step<0, 4>(acc, it, s, rb0, rb1, rb2, rb3, lane, Wst, Yfrag, full_bar, empty_bar);
+                    fast_step<0, 3>(acc, it, s, rb0, rb1, rb2, rb3, lane, Wst, Yfrag, full_bar, empty_bar);   // s = w
+                    ++s; ++it;
 #pragma unroll 1
-                    for (; kc <= rb1; ++kc, ++it) fast_chunk<1>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+                    for (; s < rb1; ++s, ++it) fast_step<1, 3>(acc, it, s, rb0, rb1, rb2, rb3, lane, Wst, Yfrag, full_bar, empty_bar);
+                    if (s == rb1) {                                                                          // s = 15 - w
+                        fast_step<1, 2>(acc, it, s, rb0, rb1, rb2, rb3, lane, Wst, Yfrag, full_bar, empty_bar);
+                        ++s; ++it;
+                    }
 #pragma unroll 1
-                    for (; kc <= rb2; ++kc, ++it) fast_chunk<2>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
-#pragma unroll 1
-                    for (; kc <= rb3; ++kc, ++it) fast_chunk<3>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
-#pragma unroll 1
-                    for (; kc < MAX_NRB; ++kc, ++it) fast_chunk<4>(acc, it, kc, rb0, rb1, rb2, rb3, lane, Wst, Dst, full_bar, empty_bar);
+                    for (; s < MAX_NRB / 2; ++s, ++it) fast_step<2, 2>(acc, it, s, rb0, rb1, rb2, rb3, lane, Wst, Yfrag, full_bar, empty_bar);
                 } else {
                     // generic path (T < 256): row blocks tested per chunk
-                    for (int kc = 0; kc < nrb; ++kc, ++it) {
-                        const int stage = it & (STAGES - 1);
+                    for (int s = 0; s < n_steps; ++s, ++it) {
+                        const int stage = it % STAGES;
                         mbar_wait(&full_bar[stage], (it / STAGES) & 1);
-                        if (31 - warp >= kc) {   // rb_3 = 31 - w is this warp's largest block
-                            const double2* ds = reinterpret_cast<const double2*>(Dst + stage * D_STAGE_BYTES) + lane;
+                        const int ka = s, kb = nrb - 1 - s;
+#pragma unroll 1
+                        for (int half = 0; half < 2; ++half) {
+                            const int kc = half ? kb : ka;
+                            if (half && kb <= ka) break;
+                            if (31 - warp < kc) continue;   // rb_3 = 31 - w is this warp's largest block
+                            const double2* ys = reinterpret_cast<const double2*>(Yfrag + kc * Y_CHUNK_DOUBLES) + lane;
                             double2 b[8];
 #pragma unroll
-                            for (int nt = 0; nt < 8; ++nt) b[nt] = ds[nt * 32];
-                            const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane;
+                            for (int nt = 0; nt < 8; ++nt) b[nt] = ys[nt * 32];
+                            const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane +
+                                                (half ? (nrb - ka) * 32 : 0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int rb = (j & 1) ? (8 * j + 7 - warp) : (8 * j + warp);
@@ -320,9 +300,9 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                                 if (rb >= kc && rb < nrb) {
                                     const double2 a = ws[(rb - kc) * 32];
 #pragma unroll
-                                    for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a.x, b[nt].x);
+                                    for (int nt = 0; nt < 8; ++nt) tile_mma(acc[j][nt][0], acc[j][nt][1], a.x, b[nt].x);
 #pragma unroll
-                                    for (int nt = 0; nt < 8; ++nt) dmma884(acc[j][nt][0], acc[j][nt][1], a.y, b[nt].y);
+                                    for (int nt = 0; nt < 8; ++nt) tile_mma(acc[j][nt][0], acc[j][nt][1], a.y, b[nt].y);
                                 }
                             }
                         }
@@ -330,20 +310,64 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                         if (lane == 0) mbar_arrive(&empty_bar[stage]);
                     }
                 }
-                // ---- epilogue: |z|^2 per beat ----
+                // ---- epilogue: z = acc - nu, |z|^2 per beat ----
                 double* rbuf = red + (epi & 1) * (NCW * BT);
                 ++epi;
+                if (st_u >= -1) {
+                    // every beat of the tile scores against the same state: one nu value per row block
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
+                    for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        double v = 0.0;
+                        for (int e = 0; e < 2; ++e) {
+                            double r = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v += acc[j][nt][e] * acc[j][nt][e];
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (lane < 4) rbuf[warp * BT + nt * 8 + 2 * lane + e] = v;
+                            for (int j = 0; j < 4; ++j) {
+                                const double d = acc[j][nt][e] - nu_r[j];
+                                r += d * d;
+                            }
+                            r += __shfl_xor_sync(0xffffffffu, r, 4);
+                            r += __shfl_xor_sync(0xffffffffu, r, 8);
+                            r += __shfl_xor_sync(0xffffffffu, r, 16);
+                            if (lane < 4) rbuf[warp * BT + nt * 8 + 2 * lane + e] = r;
+                        }
+                    }
+                } else {
+                    // the tile holds members of this cluster: one nu row per beat, gathered through L2 (16 loads in
+                    // flight per lane).  The state indices come from the st_epi loads through shared memory; this
+                    // branch is CTA-uniform, so the extra barrier is safe.
+                    int* sstate = reinterpret_cast<int*>(red + 2 * NCW * BT);
+                    if (tid < BT) sstate[tid] = st_epi;
+                    consumer_bar();
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {
+                        double g[2][2][4];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int sb = sstate[(2 * np + h) * 8 + 2 * (lane & 3) + e];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int row = rb_of[j] * 8 + qrow;
+                                    g[h][e][j] = (sb >= 0 && row < T) ? __ldg(nu + (int64_t)sb * T + row) : 0.0;
+                                }
+                            }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int nt = 2 * np + h;
+                                double r = 0.0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const double d = acc[j][nt][e] - g[h][e][j];
+                                    r += d * d;
+                                }
+                                r += __shfl_xor_sync(0xffffffffu, r, 4);
+                                r += __shfl_xor_sync(0xffffffffu, r, 8);
+                                r += __shfl_xor_sync(0xffffffffu, r, 16);
+                                if (lane < 4) rbuf[warp * BT + nt * 8 + 2 * lane + e] = r;
+                            }
                     }
                 }
                 consumer_bar();
@@ -357,8 +381,43 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                     }
                 }
             }
-            __syncthreads();   // matches the producers' end-of-item barrier
+            __syncthreads();   // matches the producer's end-of-item barrier
         }
+    }
+}
+
+// Uniform state of every (64-beat tile, cluster): the common state index if all beats of the tile (inside [0, N))
+// score against the same state of the cluster (-1 = empty cluster included), -2 otherwise.
+__global__ void tile_uniform_states_kernel(const int* __restrict__ state_of, int64_t N, int M, int64_t n_tiles,
+                                           int* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_tiles * M) return;
+    const int64_t tile = idx / M;
+    const int m = (int)(idx % M);
+    const int64_t n0 = tile * BT, n1 = hgp_min64(N, n0 + BT);
+    const int s0 = state_of[n0 * M + m];
+    int u = s0;
+    for (int64_t n = n0 + 1; n < n1; ++n)
+        if (state_of[n * M + m] != s0) { u = -2; break; }
+    out[idx] = u;
+}
+
+// nu[s] = W[factor_of_state[s]] mu[s]  (W lower triangular): one CTA per state, one warp per output row.
+__global__ void __launch_bounds__(256)
+whiten_means_kernel(const double* __restrict__ mu, const double* __restrict__ W, const int* __restrict__ factor_of_state,
+                    int T, double* __restrict__ nu) {
+    extern __shared__ double msm[];
+    const int64_t s = blockIdx.x;
+    const double* Wf = W + (int64_t)(factor_of_state ? factor_of_state[s] : s) * T * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) msm[t] = mu[s * T + t];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < T; r += blockDim.x >> 5) {
+        const double* wr = Wf + (int64_t)r * T;
+        double acc = 0.0;
+        for (int k = lane; k <= r; k += 32) acc += wr[k] * msm[k];
+        acc = warp_sum(acc);
+        if (lane == 0) nu[s * T + r] = acc;
     }
 }
 
@@ -447,6 +506,61 @@ snr_states_reg_kernel(const double* __restrict__ Y, int64_t N, int T, const doub
     }
 }
 
+// SNR statistic, tile form: consecutive beats almost always score against the SAME state of a cluster (the state index
+// only advances when that cluster gains a member), so a (32-beat tile, cluster) pair touches 1 + (#members of the
+// cluster inside the tile) distinct rows of the smoothed-mean table.  One CTA keeps the beat tile in shared memory; each
+// warp walks its clusters down the tile with the current state row in registers and reloads it (through L2) only when
+// the index changes: (M + 32) row reads per tile instead of 32 M.
+constexpr int SNR_BT = 32;
+template <int NREG>
+__global__ void __launch_bounds__(256)
+snr_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
+                 const int* __restrict__ snr_state_of, int M, double* __restrict__ snr) {
+    extern __shared__ double ytile[];      // [SNR_BT][T]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int64_t n_tiles = (N + SNR_BT - 1) / SNR_BT;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t n0 = tile * SNR_BT;
+        const int nb = (int)hgp_min64(SNR_BT, N - n0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * T; i += blockDim.x) ytile[i] = Y[n0 * T + i];
+        __syncthreads();
+        for (int m = warp; m < M; m += nwarps) {
+            const int my_s = (lane < nb) ? snr_state_of[(n0 + lane) * M + m] : -1;
+            int s_cur = -2;
+            double v[NREG], sig = 0.0;
+            double my_sig = 0.0, my_noi = 0.0;       // lane b keeps the sums of beat b: one log10 per lane, not per beat
+            for (int b = 0; b < nb; ++b) {
+                const int s = __shfl_sync(0xffffffffu, my_s, b);
+                if (s != s_cur) {
+                    s_cur = s;
+                    const double* r = mu_sm + (int64_t)max(s, 0) * T;
+                    double p = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NREG; ++k) {
+                        const int t = lane + 32 * k;
+                        v[k] = (s >= 0 && t < T) ? __ldg(r + t) : 0.0;
+                        p += v[k] * v[k];
+                    }
+                    sig = warp_sum(p);
+                }
+                const double* y = ytile + b * T;
+                double noi = 0.0;
+#pragma unroll
+                for (int k = 0; k < NREG; ++k) {
+                    const int t = lane + 32 * k;
+                    const double d = (t < T) ? v[k] - y[t] : 0.0;
+                    noi += d * d;
+                }
+                noi = warp_sum(noi);
+                if (lane == b) { my_sig = sig; my_noi = noi; }
+            }
+            if (lane < nb)
+                snr[(n0 + lane) * M + m] = (my_s >= 0) ? 10.0 * log10((my_sig + HGP_EPS) / (my_noi + HGP_EPS)) : 0.0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 snr_states_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
                   const int* __restrict__ snr_state_of, int M, double* __restrict__ snr) {
@@ -479,8 +593,31 @@ snr_states_kernel(const double* __restrict__ Y, int64_t N, int T, const double* 
 
 }  // namespace
 
-extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* mu, const double* Wpacked,
-                               const int* state_of, const int* factor_of_cluster, int M, double* q,
+extern "C" int hgp_tile_beats(void) { return BT; }
+
+extern "C" int hgp_tile_uniform_states(const int* state_of, int64_t N, int M, int* tile_state, void* stream) {
+    HGP_REQUIRE(N >= 0 && M >= 0, "hgp_tile_uniform_states: bad sizes");
+    if (N == 0 || M == 0) return 0;
+    const int64_t n_tiles = (N + BT - 1) / BT;
+    const int64_t n = n_tiles * M;
+    tile_uniform_states_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state_of, N, M, n_tiles,
+                                                                                            tile_state);
+    HGP_LAUNCH_CHECK("hgp_tile_uniform_states");
+    return 0;
+}
+
+extern "C" int hgp_whiten_means(const double* mu, const double* W, const int* factor_of_state, int64_t S, int T,
+                                double* nu, void* stream) {
+    HGP_REQUIRE(S >= 0 && T > 0 && T <= 4096, "hgp_whiten_means: bad sizes");
+    if (S == 0) return 0;
+    HGP_REQUIRE(S < (1ll << 31), "hgp_whiten_means: too many states for one launch");
+    whiten_means_kernel<<<(unsigned)S, 256, sizeof(double) * T, (cudaStream_t)stream>>>(mu, W, factor_of_state, T, nu);
+    HGP_LAUNCH_CHECK("hgp_whiten_means");
+    return 0;
+}
+
+extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* nu, const double* Wpacked,
+                               const int* state_of, const int* tile_state, const int* factor_of_cluster, int M, double* q,
                                const double* mu_sm, const int* snr_state_of, double* snr, void* stream) {
     HGP_REQUIRE(N >= 0 && M >= 0, "hgp_score_tiles: bad sizes");
     HGP_REQUIRE(snr == nullptr || (mu_sm != nullptr && snr_state_of != nullptr), "hgp_score_tiles: snr needs mu_sm and snr_state_of");
@@ -494,7 +631,7 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
         if (n_sm <= 0) n_sm = 148;
     }
     const int nrb = (T + 7) / 8;
-    const TileSmem lay = tile_smem_layout(nrb * 8);
+    const TileSmem lay = tile_smem_layout(nrb);
     cudaError_t e = cudaFuncSetAttribute(score_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
     if (e != cudaSuccess) return hgp_status(e, "hgp_score_tiles: smem attribute");
     const int64_t n_tiles = (N + BT - 1) / BT;
@@ -506,8 +643,8 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
     const int64_t n_items = n_tiles * m_splits;
     const int grid = (int)hgp_min64(n_items, n_sm);
     score_tiles_kernel<<<grid, TILE_THREADS, lay.total, (cudaStream_t)stream>>>(
-        Y, N, T, mu, Wpacked, hgp_packed_factor_bytes(T) / 8, state_of, factor_of_cluster, M, m_per_item, m_splits,
-        n_items, q, mu_sm, snr_state_of, snr);
+        Y, N, T, nu, Wpacked, hgp_packed_factor_bytes(T) / 8, state_of, tile_state, factor_of_cluster, M, m_per_item,
+        m_splits, n_items, q);
     HGP_LAUNCH_CHECK("hgp_score_tiles");
     if (snr) return hgp_snr_states(Y, N, T, mu_sm, snr_state_of, M, snr, stream);
     return 0;
@@ -544,10 +681,15 @@ extern "C" int hgp_snr_states(const double* Y, int64_t N, int T, const double* m
         if (e != cudaSuccess) return hgp_status(e, "hgp_snr_states: smem attribute");
     }
     int blocks = (int)hgp_min64((N + warps - 1) / warps, 148 * 8);
-    if (T <= 128) {
-        snr_states_reg_kernel<4><<<blocks, warps * 32, 0, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
-    } else if (T <= 256) {
-        snr_states_reg_kernel<8><<<blocks, warps * 32, 0, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
+    if (T <= 256) {
+        const size_t tsm = sizeof(double) * SNR_BT * T;          // <= 64 KB: three CTAs per SM
+        const int tblocks = (int)hgp_min64((N + SNR_BT - 1) / SNR_BT, 148 * 3);
+        auto kern = T <= 128 ? snr_tiles_kernel<4> : snr_tiles_kernel<8>;
+        if (tsm > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+            if (e != cudaSuccess) return hgp_status(e, "hgp_snr_states: smem attribute");
+        }
+        kern<<<tblocks, warps * 32, tsm, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
     } else {
         snr_states_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
     }

@@ -87,6 +87,8 @@ class LeadTables:
         M = state_of.shape[1]
         self.N, self.T, self.M = N, T, M
         self.Wpacked = None
+        self.nu = None                              # [S, T] whitened means W mu (tile path)
+        self.tile_state = None                      # [ceil(N / 64), M] uniform state per (tile, cluster) or -2
         self.factor_of_cluster = None
         self.pair_n = self.pair_m = None
         self.use_tiles = False
@@ -109,6 +111,8 @@ class LeadTables:
         self.use_tiles = True
         self.factor_of_cluster = main_c.to(I32).contiguous()
         self.Wpacked = ops.pack_factors(self.W)
+        self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
+        self.tile_state = ops.tile_uniform_states(self.state_of)
         if n_exc:
             nz = torch.nonzero(exc)
             self.pair_n = nz[:, 0].to(I32).contiguous()
@@ -118,8 +122,8 @@ class LeadTables:
         """q (and, when snr_out is given, the SNR statistic) for this lead plane."""
         if self.use_tiles:
             fuse = snr_out is not None and self.snr_state_of is not None
-            ops.score_tiles(self.Y, self.mu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out,
-                            mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of if fuse else None,
+            ops.score_tiles(self.Y, self.nu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out,
+                            tile_state=self.tile_state, mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of if fuse else None,
                             snr_out=snr_out if fuse else None)
             if self.pair_n is not None:
                 ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m,

@@ -84,14 +84,41 @@ def emission_means(C, f, c_idx, f_idx):
     return mu
 
 
-def score_tiles(Y, mu, Wpacked, state_of, factor_of_cluster, out=None, mu_sm=None, snr_state_of=None, snr_out=None):
-    """Tensor-core tile scoring; with (mu_sm, snr_state_of, snr_out) the SNR statistic is fused in."""
+def tile_uniform_states(state_of):
+    """Per (64-beat tile, cluster): the state shared by all beats of the tile, or -2 (see hgp_tile_uniform_states)."""
+    lib = _lib_ready()
+    so = _dev(state_of).contiguous()
+    N, M = so.shape
+    bt = int(lib.hgp_tile_beats())
+    out = torch.empty(((N + bt - 1) // bt, M), dtype=I32, device=so.device)
+    check(lib.hgp_tile_uniform_states(ptr(so), N, M, ptr(out), stream_ptr()), "hgp_tile_uniform_states")
+    return out
+
+
+def whiten_means(mu, W, factor_of_state=None):
+    """nu[s] = W[factor_of_state[s]] mu[s]: the state means in the whitened coordinates the tile kernel works in."""
+    lib = _lib_ready()
+    mu = _dev(mu).contiguous()
+    W = _dev(W).contiguous()
+    S, T = mu.shape
+    nu = torch.empty_like(mu)
+    if factor_of_state is not None:
+        factor_of_state = _dev(factor_of_state).to(I32).contiguous()
+    check(lib.hgp_whiten_means(ptr(mu), ptr(W), ptr(factor_of_state), S, T, ptr(nu), stream_ptr()), "hgp_whiten_means")
+    return nu
+
+
+def score_tiles(Y, nu, Wpacked, state_of, factor_of_cluster, out=None, tile_state=None, mu_sm=None, snr_state_of=None,
+                snr_out=None):
+    """Tensor-core emission scores of one lead plane; nu = whiten_means(mu, W, factor_of_state)."""
     lib = _lib_ready()
     N, T = Y.shape
     M = state_of.shape[1]
     q = out if out is not None else torch.empty((N, M), dtype=F64, device=Y.device)
-    check(lib.hgp_score_tiles(ptr(Y), N, T, ptr(mu), ptr(Wpacked), ptr(state_of), ptr(factor_of_cluster), M, ptr(q),
-                              ptr(mu_sm), ptr(snr_state_of), ptr(snr_out), stream_ptr()), "hgp_score_tiles")
+    if tile_state is None:
+        tile_state = tile_uniform_states(state_of)
+    check(lib.hgp_score_tiles(ptr(Y), N, T, ptr(nu), ptr(Wpacked), ptr(state_of), ptr(tile_state), ptr(factor_of_cluster),
+                              M, ptr(q), ptr(mu_sm), ptr(snr_state_of), ptr(snr_out), stream_ptr()), "hgp_score_tiles")
     return q
 
 

@@ -70,15 +70,25 @@ int hgp_pack_factors(const double* W, int64_t F, int T, double* Wpacked, void* s
  *                                       :626-662; -1 => q = 0, "cluster has no members" :494-495)
  *     q[n*M + m] = -0.5 * | W_f (Y[n] - mu[s]) |^2 - 0.5 * T * log(2 pi)        (no log-det)
  *
- * hgp_score_tiles: f = factor_of_cluster[m]; all beats, W in packed form; tensor-core (DMMA) path.
- *                  When snr != NULL the SNR lead statistic of hgp_snr_states (below) is fused into the
- *                  same pass (the producer warps that stage y - mu also accumulate it).
+ * hgp_score_tiles: f = factor_of_cluster[m]; all beats, W in packed form; tensor-core (DMMA) path.  Takes the
+ *                  WHITENED state means nu[s] = W_f mu[s] (hgp_whiten_means) and evaluates |W_f Y[n] - nu[s]|^2: the
+ *                  matrix product runs on the beats alone (one B operand for all clusters) and the mean is
+ *                  subtracted in the epilogue.  tile_state (hgp_tile_uniform_states) tells the kernel which
+ *                  (64-beat tile, cluster) items use one state for all their beats.  When snr != NULL the SNR lead
+ *                  statistic of hgp_snr_states (below) is launched behind it on the same stream.
  * hgp_score_pairs: explicit list of (n, m) pairs with f = factor_of_state[s]; W in plain form;
  *                  used for the states whose covariance differs from the cluster's shared one
  *                  (per-state Sigma_i when estimation_limit=None, the `first` jitter) and as the
  *                  general path when every state has its own factor. */
-int hgp_score_tiles(const double* Y, int64_t N, int T, const double* mu, const double* Wpacked,
-                    const int* state_of, const int* factor_of_cluster, int M, double* q,
+int hgp_tile_beats(void);   /* beats per tile of hgp_score_tiles / hgp_tile_uniform_states (64) */
+/* tile_state[tile*M + m] = the state index shared by all beats of tile `tile` for cluster m (-1: empty cluster),
+ * or -2 when they differ.  tile_state: ceil(N / hgp_tile_beats()) * M ints. */
+int hgp_tile_uniform_states(const int* state_of, int64_t N, int M, int* tile_state, void* stream);
+/* nu[s] = W[factor_of_state[s]] mu[s] for s in [0, S)  (factor_of_state NULL: factor s). */
+int hgp_whiten_means(const double* mu, const double* W, const int* factor_of_state, int64_t S, int T, double* nu,
+                     void* stream);
+int hgp_score_tiles(const double* Y, int64_t N, int T, const double* nu, const double* Wpacked,
+                    const int* state_of, const int* tile_state, const int* factor_of_cluster, int M, double* q,
                     const double* mu_sm, const int* snr_state_of, double* snr, void* stream);
 int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const double* W,
                     const int* state_of, const int* factor_of_state, int M,

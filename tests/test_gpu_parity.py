@@ -676,7 +676,7 @@ def test_full_size_properties():
     a = eng.q[0][pn.long(), pm.long()]; b = chk[pn.long(), pm.long()]
     assert float(torch.max(torch.abs(a - b) / torch.abs(b))) < 1e-11
     perm = torch.randperm(N, device="cuda", generator=g)
-    q_perm = ops.score_tiles(tb.Y[perm].contiguous(), tb.mu, tb.Wpacked, tb.state_of[perm].contiguous(),
+    q_perm = ops.score_tiles(tb.Y[perm].contiguous(), tb.nu, tb.Wpacked, tb.state_of[perm].contiguous(),
                              tb.factor_of_cluster)
     keep = torch.ones((N, M), dtype=torch.bool, device="cuda")
     if tb.pair_n is not None:

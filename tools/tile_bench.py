@@ -16,13 +16,13 @@ res = {"lib": os.environ.get("HGP_LIB", "default"), "beats": B}
 for fused in (False, True):
     kw = dict(mu_sm=tb.mu_sm, snr_state_of=tb.snr_state_of, snr_out=eng.snr[0]) if fused else {}
     for _ in range(3):
-        ops.score_tiles(tb.Y, tb.mu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[0], **kw)
+        ops.score_tiles(tb.Y, tb.nu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[0], tile_state=tb.tile_state, **kw)
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.score_tiles(tb.Y, tb.mu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[0], **kw)
+        ops.score_tiles(tb.Y, tb.nu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[0], tile_state=tb.tile_state, **kw)
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     res["fused_ms" if fused else "plain_ms"] = best
