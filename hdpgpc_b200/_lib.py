@@ -31,6 +31,8 @@ PROTOTYPES = {
     "hgp_hmm_workspace_bytes": (_i64, [_i64, _int]),
     "hgp_hmm_smooth": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p, _p, _i64,
                               _c.POINTER(_int), _p]),
+    "hgp_hmm_resmooth": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p, _p, _i64,
+                              _c.POINTER(_int), _p]),
     "hgp_suffstats_workspace_bytes": (_i64, [_i64, _int]),
     "hgp_suffstats": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _i64, _p]),
     "hgp_qlat_workspace_bytes": (_i64, [_i64, _int]),

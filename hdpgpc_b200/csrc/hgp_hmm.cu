@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(4 * KP)
 hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __restrict__ pi,
                 const double* __restrict__ Mat, const double* __restrict__ boundary, int has_boundary,
                 double* __restrict__ msgs, double* __restrict__ marg, const double* __restrict__ ends_in,
-                double* __restrict__ ends_out, int* __restrict__ changed, int repair) {
+                double* __restrict__ ends_out, int* __restrict__ changed, int repair, int rebase) {
     constexpr int SEG = KP / 4;
     constexpr int NW = (4 * KP + 31) / 32;
     __shared__ double s_prev[KP];      // forward: alpha_{t-1};  backward: u_{t+1} = beta_{t+1} * e_{t+1}
@@ -96,7 +96,9 @@ hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __
 
     // the chunk whose start is exact by construction
     const bool exact_start = BACKWARD ? (c == C - 1) : (c == 0);
-    if (repair && exact_start) {
+    // rebase: the message ENTERING the slice changed since the stored solution was computed (sharded scan: the
+    // neighbour rank's boundary arrived), so the boundary chunk is repaired like any other chunk
+    if (repair && exact_start && !rebase) {
         if (tid < K) ends_out[c * K + tid] = ends_in[c * K + tid];
         return;
     }
@@ -312,33 +314,37 @@ __global__ void stats_finish_kernel(const int* __restrict__ counts, const double
 template <int KP>
 int launch_scans(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
                  const double* boundary_in, int has_prev, int has_next, double* alpha, double* beta, double* marg,
-                 double* endsA, double* endsB, int* changed, int* changed_host, int* rounds_host, cudaStream_t st) {
+                 double* endsA, double* endsB, int* changed, int* changed_host, int* rounds_host, cudaStream_t st,
+                 int warm) {
     const int64_t C = (N + CHUNK - 1) / CHUNK;
     const int threads = 4 * KP;
     double* fa[2] = {endsA, endsA + C * K};
     double* fb[2] = {endsB, endsB + C * K};
     cudaMemsetAsync(changed, 0, 2 * sizeof(int), st);
+    if (!warm) {
     hmm_scan_kernel<KP, false><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, PiT, boundary_in, has_prev, alpha,
-                                                                 marg, nullptr, fa[0], changed, 0);
+                                                                 marg, nullptr, fa[0], changed, 0, 0);
     HGP_LAUNCH_CHECK("hmm forward scan");
     hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr,
-                                                                has_next, beta, nullptr, nullptr, fb[0], changed + 1, 0);
+                                                                has_next, beta, nullptr, nullptr, fb[0], changed + 1, 0, 0);
     HGP_LAUNCH_CHECK("hmm backward scan");
+    }
     int rounds = 0;
-    if (C > 1) {
+    if (C > 1 || warm) {
         int cur = 0;
         bool need_f = true, need_b = true;
+        int first_rebase = warm;     // warm start: the first repair round also re-scans the two boundary chunks
         while (need_f || need_b) {
             cudaMemsetAsync(changed, 0, 2 * sizeof(int), st);
             if (need_f) {
                 hmm_scan_kernel<KP, false><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, PiT, boundary_in, has_prev,
-                                                                             alpha, marg, fa[cur], fa[cur ^ 1], changed, 1);
+                                                                             alpha, marg, fa[cur], fa[cur ^ 1], changed, 1, first_rebase);
                 HGP_LAUNCH_CHECK("hmm forward repair");
             }
             if (need_b) {
                 hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, st>>>(
                     e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr, has_next, beta, nullptr, fb[cur], fb[cur ^ 1],
-                    changed + 1, 1);
+                    changed + 1, 1, first_rebase);
                 HGP_LAUNCH_CHECK("hmm backward repair");
             }
             cudaError_t er = cudaMemcpyAsync(changed_host, changed, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -355,6 +361,7 @@ int launch_scans(const double* e, int64_t N, int K, const double* pi, const doub
             if (!need_b) cudaMemcpyAsync(fb[cur ^ 1], fb[cur], sizeof(double) * C * K, cudaMemcpyDeviceToDevice, st);
             need_f = cf;
             need_b = cb;
+            first_rebase = 0;
             cur ^= 1;
             if (rounds > C + 2) { hgp_set_error("hmm repair did not converge"); return HGP_E_UNSUPPORTED; }
         }
@@ -389,7 +396,7 @@ extern "C" int64_t hgp_hmm_workspace_bytes(int64_t N, int K) {
     return 4 * C * K * (int64_t)sizeof(double) + 256;
 }
 
-extern "C" int hgp_hmm_smooth(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
+static int hmm_smooth_impl(int warm, const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
                               const double* Pc, const double* boundary_in, int has_prev, int has_next, double* alpha,
                               double* beta, double* marg, int* z, int* zpair, double* boundary_out, void* workspace,
                               int64_t workspace_bytes, int* rounds_host, void* stream) {
@@ -404,11 +411,11 @@ extern "C" int hgp_hmm_smooth(const double* e, int64_t N, int K, const double* p
     int* changed = reinterpret_cast<int*>(endsB + 2 * C * K);
     int changed_host[2] = {0, 0};
     int rc;
-    if (K <= 8) rc = launch_scans<8>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st);
-    else if (K <= 16) rc = launch_scans<16>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st);
-    else if (K <= 32) rc = launch_scans<32>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st);
-    else if (K <= 64) rc = launch_scans<64>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st);
-    else rc = launch_scans<128>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st);
+    if (K <= 8) rc = launch_scans<8>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st, warm);
+    else if (K <= 16) rc = launch_scans<16>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st, warm);
+    else if (K <= 32) rc = launch_scans<32>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st, warm);
+    else if (K <= 64) rc = launch_scans<64>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st, warm);
+    else rc = launch_scans<128>(e, N, K, pi, PiT, Pi, boundary_in, has_prev, has_next, alpha, beta, marg, endsA, endsB, changed, changed_host, rounds_host, st, warm);
     if (rc) return rc;
     const int warps = 8;
     size_t smem = sizeof(double) * warps * 2 * K;
@@ -423,6 +430,22 @@ extern "C" int hgp_hmm_smooth(const double* e, int64_t N, int K, const double* p
         if (er != cudaSuccess) return hgp_status(er, "hgp_hmm_smooth: boundary copy");
     }
     return 0;
+}
+
+extern "C" int hgp_hmm_smooth(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
+                              const double* Pc, const double* boundary_in, int has_prev, int has_next, double* alpha,
+                              double* beta, double* marg, int* z, int* zpair, double* boundary_out, void* workspace,
+                              int64_t workspace_bytes, int* rounds_host, void* stream) {
+    return hmm_smooth_impl(0, e, N, K, pi, PiT, Pi, Pc, boundary_in, has_prev, has_next, alpha, beta, marg, z, zpair,
+                           boundary_out, workspace, workspace_bytes, rounds_host, stream);
+}
+
+extern "C" int hgp_hmm_resmooth(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
+                                const double* Pc, const double* boundary_in, int has_prev, int has_next, double* alpha,
+                                double* beta, double* marg, int* z, int* zpair, double* boundary_out, void* workspace,
+                                int64_t workspace_bytes, int* rounds_host, void* stream) {
+    return hmm_smooth_impl(1, e, N, K, pi, PiT, Pi, Pc, boundary_in, has_prev, has_next, alpha, beta, marg, z, zpair,
+                           boundary_out, workspace, workspace_bytes, rounds_host, stream);
 }
 
 extern "C" int64_t hgp_suffstats_workspace_bytes(int64_t N, int K) {

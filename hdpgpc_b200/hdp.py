@@ -145,7 +145,8 @@ def sharded_hmm_exchange(smooth, K, rank, world, group, device):
     scanned again; repeat until no boundary moves BITWISE.  The recursion is a deterministic function of
     the incoming message, so the fixed point equals the sequential scan bit for bit.
 
-    smooth(boundary_in[2K], has_prev, has_next) -> result with .boundary_out[2K] (device tensor)."""
+    smooth(boundary_in[2K], has_prev, has_next, prev) -> result with .boundary_out[2K] (device tensor); prev is the
+    previous round's result, to be repaired in place from the new boundary instead of scanning the slice again."""
     dist = torch.distributed
     has_prev, has_next = rank > 0, rank < world - 1
     bin_ = torch.empty(2 * K, dtype=F64, device=device)
@@ -154,8 +155,9 @@ def sharded_hmm_exchange(smooth, K, rank, world, group, device):
     gathered_flat = torch.empty(world * 2 * K, dtype=F64, device=device)   # 1-D: accepted by nccl and gloo alike
     gathered = gathered_flat.view(world, 2 * K)
     rounds = 0
+    hm = None
     while True:
-        hm = smooth(bin_, has_prev, has_next)
+        hm = smooth(bin_, has_prev, has_next, hm)
         dist.all_gather_into_tensor(gathered_flat, hm.boundary_out.contiguous(), group=group)
         new_in = bin_.clone()
         if has_prev:
@@ -226,9 +228,9 @@ class EStepEngine:
         return qbar, e, w, hm
 
     def _hmm_sharded(self, e):
-        smooth = lambda bin_, has_prev, has_next: ops.hmm_smooth(
+        smooth = lambda bin_, has_prev, has_next, prev=None: ops.hmm_smooth(
             e, self.pi, self.PiT, self.Pi, self.Pc, boundary_in=bin_, has_prev=has_prev, has_next=has_next,
-            workspace=self._hmm_ws)
+            workspace=self._hmm_ws, prev=prev)
         hm, rounds = sharded_hmm_exchange(smooth, self.M, self.rank, self.world, self.group, self.device)
         self.boundary_rounds = rounds
         return hm

@@ -157,29 +157,37 @@ def lead_weights(q_lnm, snr_lnm=None, lead_w=None):
 
 
 class HmmResult:
-    __slots__ = ("alpha", "beta", "marg", "z", "zpair", "boundary_out", "rounds")
+    __slots__ = ("alpha", "beta", "marg", "z", "zpair", "boundary_out", "rounds", "workspace")
 
 
-def hmm_smooth(e, pi, PiT, Pi, Pc, boundary_in=None, has_prev=False, has_next=False, workspace=None):
+def hmm_smooth(e, pi, PiT, Pi, Pc, boundary_in=None, has_prev=False, has_next=False, workspace=None, prev=None):
+    """HMM smoothing + hard responsibilities of one beat slice.  prev: the HmmResult of an earlier call on the SAME e
+    with another boundary_in -- its arrays are repaired in place (hgp_hmm_resmooth) instead of scanning the slice again."""
     lib = _lib_ready()
     N, K = e.shape
     dev = e.device
-    r = HmmResult()
-    r.alpha = torch.empty((N, K), dtype=F64, device=dev)
-    r.beta = torch.empty((N, K), dtype=F64, device=dev)
-    r.marg = torch.empty(N, dtype=F64, device=dev)
-    r.z = torch.empty(N, dtype=I32, device=dev)
-    r.zpair = torch.empty(N, dtype=I32, device=dev)
-    r.boundary_out = torch.empty(2 * K, dtype=F64, device=dev)
-    need = lib.hgp_hmm_workspace_bytes(N, K)
-    if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    if prev is not None:
+        r = prev
+        workspace = prev.workspace
+        fn, name = lib.hgp_hmm_resmooth, "hgp_hmm_resmooth"
+    else:
+        r = HmmResult()
+        r.alpha = torch.empty((N, K), dtype=F64, device=dev)
+        r.beta = torch.empty((N, K), dtype=F64, device=dev)
+        r.marg = torch.empty(N, dtype=F64, device=dev)
+        r.z = torch.empty(N, dtype=I32, device=dev)
+        r.zpair = torch.empty(N, dtype=I32, device=dev)
+        r.boundary_out = torch.empty(2 * K, dtype=F64, device=dev)
+        need = lib.hgp_hmm_workspace_bytes(N, K)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        r.workspace = workspace
+        fn, name = lib.hgp_hmm_smooth, "hgp_hmm_smooth"
     rounds = ctypes.c_int(0)
-    check(lib.hgp_hmm_smooth(ptr(e), N, K, ptr(pi), ptr(PiT), ptr(Pi), ptr(Pc), ptr(boundary_in), int(has_prev),
-                             int(has_next), ptr(r.alpha), ptr(r.beta), ptr(r.marg), ptr(r.z), ptr(r.zpair),
-                             ptr(r.boundary_out), ptr(workspace), workspace.numel(), ctypes.byref(rounds),
-                             stream_ptr()), "hgp_hmm_smooth")
-    r.rounds = rounds.value
+    check(fn(ptr(e), N, K, ptr(pi), ptr(PiT), ptr(Pi), ptr(Pc), ptr(boundary_in), int(has_prev), int(has_next),
+             ptr(r.alpha), ptr(r.beta), ptr(r.marg), ptr(r.z), ptr(r.zpair), ptr(r.boundary_out), ptr(workspace),
+             workspace.numel(), ctypes.byref(rounds), stream_ptr()), name)
+    r.rounds = rounds.value if prev is None else max(r.rounds, rounds.value)
     return r
 
 

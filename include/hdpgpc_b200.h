@@ -126,6 +126,14 @@ int hgp_hmm_smooth(const double* e, int64_t N, int K, const double* pi, const do
                    const double* Pc, const double* boundary_in, int has_prev, int has_next,
                    double* alpha, double* beta, double* marg, int* z, int* zpair, double* boundary_out,
                    void* workspace, int64_t workspace_bytes, int* rounds_host, void* stream);
+/* Same outputs as hgp_hmm_smooth for a CHANGED boundary_in, given that alpha / beta / marg / workspace still hold the
+ * result of a previous call on the same e: only the chunks the new boundary messages actually alter are scanned again
+ * (the boundary chunk first, then onwards until a recomputed message equals the stored one bitwise).  This is the
+ * second and later rounds of the sharded boundary exchange: a full re-scan of the slice would double the HMM cost. */
+int hgp_hmm_resmooth(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
+                   const double* Pc, const double* boundary_in, int has_prev, int has_next,
+                   double* alpha, double* beta, double* marg, int* z, int* zpair, double* boundary_out,
+                   void* workspace, int64_t workspace_bytes, int* rounds_host, void* stream);
 
 /* ---- sufficient statistics: include_batch (GPI_HDP.py:890-892), compute_q_elbo (:1805) --------
  * Nm[K] = sum_n [z_n = k];  trans[K,K] = sum_n onehot(zpair_n) (counts, exact integers in f64);

@@ -634,9 +634,12 @@ def test_sharded_hmm_emulated_ranks_bitwise():
     full = ops.hmm_smooth(e, pi, PiT, Pi, Pc)
     bounds = [0, 1000, 1700, 3100, N]
     bin_ = [torch.cat([torch.full((K,), 1.0 / K), torch.ones(K)]).double().cuda() for _ in range(G)]
+    slices = [e[bounds[g]:bounds[g + 1]].contiguous() for g in range(G)]
+    res = [None] * G
     for rounds in range(1, 10):
-        res = [ops.hmm_smooth(e[bounds[g]:bounds[g + 1]].contiguous(), pi, PiT, Pi, Pc, boundary_in=bin_[g],
-                              has_prev=g > 0, has_next=g < G - 1) for g in range(G)]
+        # round 1 scans every slice; later rounds repair the stored solution from the changed boundary (hgp_hmm_resmooth)
+        res = [ops.hmm_smooth(slices[g], pi, PiT, Pi, Pc, boundary_in=bin_[g], has_prev=g > 0, has_next=g < G - 1,
+                              prev=res[g]) for g in range(G)]
         new = []
         for g in range(G):
             b = bin_[g].clone()
@@ -653,6 +656,15 @@ def test_sharded_hmm_emulated_ranks_bitwise():
     assert torch.equal(alpha, full.alpha) and torch.equal(beta, full.beta)
     assert torch.equal(torch.cat([r.z for r in res]), full.z)
     assert torch.equal(torch.cat([r.zpair for r in res]), full.zpair)
+    # a single-chunk slice (N < 256) repaired from a changed boundary equals a cold scan with that boundary
+    e1 = e[:100].contiguous()
+    b0 = torch.cat([torch.full((K,), 1.0 / K), torch.ones(K)]).double().cuda()
+    b1 = torch.cat([full.alpha[777], full.beta[1234] * e[1234]]).contiguous()
+    warm = ops.hmm_smooth(e1, pi, PiT, Pi, Pc, boundary_in=b0, has_prev=True, has_next=True)
+    warm = ops.hmm_smooth(e1, pi, PiT, Pi, Pc, boundary_in=b1, has_prev=True, has_next=True, prev=warm)
+    cold = ops.hmm_smooth(e1, pi, PiT, Pi, Pc, boundary_in=b1, has_prev=True, has_next=True)
+    assert torch.equal(warm.alpha, cold.alpha) and torch.equal(warm.beta, cold.beta) and torch.equal(warm.z, cold.z)
+    assert torch.equal(warm.zpair, cold.zpair) and torch.equal(warm.boundary_out, cold.boundary_out)
 
 
 # ---------------------------------------------------------------------------------------------

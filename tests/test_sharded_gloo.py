@@ -56,7 +56,7 @@ def _worker(rank, world, port, q_all, tt, st, out_dir):
     e_all = O._safe_exp_rows(O.loglik_normalise(q_all))
     bounds = np.linspace(0, N, world + 1).astype(int)
     e = e_all[bounds[rank]:bounds[rank + 1]]
-    smooth = lambda b, hp, hn: _slice_smooth(e, pi, PiT, Pi, b.numpy(), hp, hn)
+    smooth = lambda b, hp, hn, prev=None: _slice_smooth(e, pi, PiT, Pi, b.numpy(), hp, hn)
     hm, rounds = hdp.sharded_hmm_exchange(smooth, K, rank, world, None, torch.device("cpu"))
     # statistics all-reduce (counts are integers -> exact in any order)
     z = np.argmax(hm.alpha * hm.beta, axis=1)
