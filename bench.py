@@ -296,6 +296,13 @@ def run_ours(args):
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None      # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu --set full capture
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_score_tiles_ncu.json")))
+            if args.config == "cfg4" and B == CFG["beats_per_gpu"]:
+                traffic = prof["dram_bytes_per_launch"]
+        except Exception:
+            pass
         bytes_launch = B * T * 8 + B * M * 8 + B * M * 4 + eng.leads[0].mu.numel() * 8 + eng.leads[0].Wpacked.numel() * 8
         cpu = None
         if not args.no_cpu:
@@ -309,7 +316,7 @@ def run_ours(args):
             "config": {"workload": workload_name(B, T, L, M), "beats_total": world * B, "l2": f"inputs_exceed_l2 (beats {B * T * L * 8 / 1e6:.0f} MB + whitened means {sum(tb.nu.numel() for tb in eng.leads) * 8 / 1e6:.0f} MB per GPU vs 126 MB L2)",
                        "label_accuracy": acc, "hmm_repair_rounds": eng.hmm_rounds, "boundary_rounds": eng.boundary_rounds},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "score_tiles_kernel", "kernel_ms": tile_ms,
+                         "traffic": traffic, "kernel": "score_tiles_kernel", "kernel_ms": tile_ms,
                          "kernel_share_of_step": L * tile_ms / ms, "flops_per_launch": flops_launch,
                          "peak_source": "cuBLAS DGEMM 8192^3 float64 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure)" if peak_sust else "nominal",
                          "peak_burst": peak_burst,
