@@ -223,73 +223,139 @@ static __device__ __noinline__ int la_chol(double* A, int T, LaSmem& sm) {
 }
 
 // ---- triangular solves with T right-hand sides (in place on B) --------------------------------------
-// B <- L^{-1} B  (forward substitution), L lower triangular
-static __device__ __noinline__ void la_trsm_lower(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
-    const int tid = threadIdx.x;
-    for (int r0 = 0; r0 < T; r0 += LA_NB) {
-        const int nb = min(LA_NB, T - r0);
-        // rows r0..r0+nb: B[i][c] -= sum_{k<r0} L[i][k] B[k][c]
-        for (int idx = tid; idx < nb * T; idx += LA_THREADS) {
-            const int i = r0 + idx / T, c = idx % T;
-            double acc = 0.0;
-            const double* lr = L + (int64_t)i * T;
-            for (int k = 0; k < r0; ++k) acc += lr[k] * B[(int64_t)k * T + c];
-            B[(int64_t)i * T + c] -= acc;
-        }
-        for (int idx = tid; idx < nb * nb; idx += LA_THREADS) sm.Dk[(idx / nb) * (LA_NB + 1) + idx % nb] = L[(int64_t)(r0 + idx / nb) * T + r0 + idx % nb];
-        __syncthreads();
-        // diagonal block: one thread per column of B
-        for (int c = tid; c < T; c += LA_THREADS) {
-            double x[LA_NB];
+// Row-block update on the tensor cores: for i in [i0, i1) (at most 64 rows) and every column c,
+//   C[i][c] += alpha * sum_{k in [k0, k1)} opA(i, k) * B[k][c],   opA(i, k) = transA ? A[k][i] : A[i][k].
+// C and B may be the same matrix as long as the row ranges [i0, i1) and [k0, k1) do not overlap.
+// Only columns c >= c_begin are touched.
+static __device__ __noinline__ void la_rows_update(double* C, const double* A, int transA, const double* B, int T, int i0,
+                                                   int i1, int k0, int k1, double alpha, LaSmem& sm, int c_begin = 0) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nct = (T + 63) / 64;
+    for (int ct = c_begin / 64; ct < nct; ++ct) {
+        const int c0 = ct * 64;
+        double acc[2][4][2];
 #pragma unroll
-            for (int i = 0; i < LA_NB; ++i) {
-                if (i < nb) {
-                    double v = B[(int64_t)(r0 + i) * T + c];
-                    for (int p = 0; p < i; ++p) v -= sm.Dk[i * (LA_NB + 1) + p] * x[p];
-                    x[i] = v / sm.Dk[i * (LA_NB + 1) + i];
-                    B[(int64_t)(r0 + i) * T + c] = x[i];
-                }
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = k0; kk < k1; kk += 16) {
+            for (int idx = tid; idx < 64 * 16; idx += LA_THREADS) {
+                int r, k;
+                if (transA) { k = idx / 64; r = idx % 64; } else { r = idx / 16; k = idx % 16; }
+                const int gr = i0 + r, gk = kk + k;
+                double v = 0.0;
+                if (gr < i1 && gk < k1) v = transA ? A[(int64_t)gk * T + gr] : A[(int64_t)gr * T + gk];
+                sm.As[r * 20 + k] = v;
             }
+            for (int idx = tid; idx < 16 * 64; idx += LA_THREADS) {
+                const int k = idx / 64, c = idx % 64;
+                const int gk = kk + k, gc = c0 + c;
+                sm.Bs[k * 72 + c] = (gk < k1 && gc < T) ? B[(int64_t)gk * T + gc] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                double a[2], bf[4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = sm.As[(16 * wm + 8 * i + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = sm.Bs[(4 * ks + (lane & 3)) * 72 + 32 * wn + 8 * j + (lane >> 2)];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gr = i0 + 16 * wm + 8 * i + (lane >> 2), gc = c0 + 32 * wn + 8 * j + 2 * (lane & 3) + e;
+                    if (gr < i1 && gc < T && gc >= c_begin) C[(int64_t)gr * T + gc] += alpha * acc[i][j][e];
+                }
     }
+    __syncthreads();
 }
-// B <- L^{-T} B  (backward substitution with the transpose of a lower-triangular L)
-static __device__ __noinline__ void la_trsm_lower_trans(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
+
+// Blocked substitution, two levels: 64-row outer blocks whose coupling to the already-solved rows is one tensor-core
+// row-block update, 16-row inner blocks solved by one thread per column of B with the diagonal block in shared memory.
+//   mode 0: B <- L^{-1} B   (L lower, forward)           mode 1: B <- L^{-T} B  (L lower, backward)
+//   mode 2: B <- L1^{-1} B  (unit lower part of an LU)   mode 3: B <- U^{-1} B  (upper part of an LU, backward)
+static __device__ __noinline__ void la_trsm_blocked(const double* __restrict__ M, double* B, int T, int mode, LaSmem& sm) {
     const int tid = threadIdx.x;
-    const int nblk = (T + LA_NB - 1) / LA_NB;
-    for (int b = nblk - 1; b >= 0; --b) {
-        const int r0 = b * LA_NB, nb = min(LA_NB, T - r0), r1 = r0 + nb;
-        // rows r0..r1: B[i][c] -= sum_{k>=r1} L[k][i] B[k][c]
-        for (int idx = tid; idx < nb * T; idx += LA_THREADS) {
-            const int i = r0 + idx / T, c = idx % T;
-            double acc = 0.0;
-            for (int k = r1; k < T; ++k) acc += L[(int64_t)k * T + i] * B[(int64_t)k * T + c];
-            B[(int64_t)i * T + c] -= acc;
-        }
-        for (int idx = tid; idx < nb * nb; idx += LA_THREADS) sm.Dk[(idx / nb) * (LA_NB + 1) + idx % nb] = L[(int64_t)(r0 + idx / nb) * T + r0 + idx % nb];
-        __syncthreads();
-        for (int c = tid; c < T; c += LA_THREADS) {
-            double x[LA_NB];
-#pragma unroll
-            for (int ii = 0; ii < LA_NB; ++ii) {
-                const int i = nb - 1 - ii;
-                if (i >= 0) {
-                    double v = B[(int64_t)(r0 + i) * T + c];
-                    for (int p = i + 1; p < nb; ++p) v -= sm.Dk[p * (LA_NB + 1) + i] * x[p];
-                    x[i] = v / sm.Dk[i * (LA_NB + 1) + i];
-                    B[(int64_t)(r0 + i) * T + c] = x[i];
+    const bool backward = (mode == 1 || mode == 3), trans = (mode == 1), unit = (mode == 2);
+    const int nouter = (T + 63) / 64;
+    for (int ob = 0; ob < nouter; ++ob) {
+        const int R0 = (backward ? nouter - 1 - ob : ob) * 64, R1 = min(T, R0 + 64);
+        if (!backward && R0 > 0) la_rows_update(B, M, 0, B, T, R0, R1, 0, R0, -1.0, sm);
+        if (backward && R1 < T) la_rows_update(B, M, trans, B, T, R0, R1, R1, T, -1.0, sm);
+        const int ninner = (R1 - R0 + LA_NB - 1) / LA_NB;
+        for (int ib = 0; ib < ninner; ++ib) {
+            const int r0 = R0 + (backward ? ninner - 1 - ib : ib) * LA_NB, nb = min(LA_NB, R1 - r0), r1 = r0 + nb;
+            // coupling to the rows of this outer block that are already solved
+            const int ka = backward ? r1 : R0, kb = backward ? R1 : r0;
+            if (kb > ka) {
+                for (int idx = tid; idx < nb * T; idx += LA_THREADS) {
+                    const int i = r0 + idx / T, c = idx % T;
+                    double acc = 0.0;
+                    for (int k = ka; k < kb; ++k)
+                        acc += (trans ? M[(int64_t)k * T + i] : M[(int64_t)i * T + k]) * B[(int64_t)k * T + c];
+                    B[(int64_t)i * T + c] -= acc;
                 }
             }
+            // diagonal block, as coef(i, p) = Dk[i][p]
+            for (int idx = tid; idx < nb * nb; idx += LA_THREADS) {
+                const int i = idx / nb, p = idx % nb;
+                sm.Dk[i * (LA_NB + 1) + p] = trans ? M[(int64_t)(r0 + p) * T + r0 + i] : M[(int64_t)(r0 + i) * T + r0 + p];
+            }
+            __syncthreads();
+            for (int c = tid; c < T; c += LA_THREADS) {
+                double x[LA_NB];
+                if (!backward) {
+#pragma unroll
+                    for (int i = 0; i < LA_NB; ++i) {
+                        if (i < nb) {
+                            double v = B[(int64_t)(r0 + i) * T + c];
+                            for (int p = 0; p < i; ++p) v -= sm.Dk[i * (LA_NB + 1) + p] * x[p];
+                            x[i] = unit ? v : v / sm.Dk[i * (LA_NB + 1) + i];
+                            B[(int64_t)(r0 + i) * T + c] = x[i];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ii = 0; ii < LA_NB; ++ii) {
+                        const int i = nb - 1 - ii;
+                        if (i >= 0) {
+                            double v = B[(int64_t)(r0 + i) * T + c];
+                            for (int p = i + 1; p < nb; ++p) v -= sm.Dk[i * (LA_NB + 1) + p] * x[p];
+                            x[i] = v / sm.Dk[i * (LA_NB + 1) + i];
+                            B[(int64_t)(r0 + i) * T + c] = x[i];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
-// ---- LU with partial pivoting (in place) and solve with T right-hand sides -----------------------------
-// piv[k] = row swapped with k at step k (global memory, T ints).  Unblocked column loop with the trailing
-// update spread over the CTA: 2/3 T^3 flops, the matrix stays in L2.
-static __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaSmem& sm) {
+// B <- L^{-1} B  (forward substitution), L lower triangular
+static __device__ __forceinline__ void la_trsm_lower(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
+    la_trsm_blocked(L, B, T, 0, sm);
+}
+// B <- L^{-T} B  (backward substitution with the transpose of a lower-triangular L)
+static __device__ __forceinline__ void la_trsm_lower_trans(const double* __restrict__ L, double* B, int T, LaSmem& sm) {
+    la_trsm_blocked(L, B, T, 1, sm);
+}
+
+// Unblocked LU for small matrices (T < LA_LU_BLOCKED_MIN: the MIT-BIH shape T = 90), where the barrier count of
+// the column loop is lower than the fixed costs of the blocked algorithm below.
+constexpr int LA_LU_BLOCKED_MIN = 160;
+static __device__ __noinline__ void la_lu_factor_small(double* A, int* piv, int T, LaSmem& sm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = 0; k < T; ++k) {
         // pivot search in column k, rows k..T-1 (first maximum of |a|, like LAPACK idamax)
@@ -336,6 +402,86 @@ static __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaS
         __syncthreads();
     }
 }
+
+// ---- LU with partial pivoting (in place) and solve with T right-hand sides -----------------------------
+// piv[k] = row swapped with k at step k (global memory, T ints).  Right-looking, panels of 16 columns:
+//   * panel (rows k0.., 16 columns = one 128-byte line per row, L1-resident): factorised by ONE warp without any
+//     CTA barrier -- pivot search by shuffle reduction (first maximum of |a|, like LAPACK idamax), swap, scale and the
+//     rank-1 updates inside the panel;
+//   * the 16 row interchanges are applied to the columns outside the panel, one thread per column;
+//   * U12 = L11^{-1} A12 (unit lower 16 x 16 block in shared memory, one thread per column);
+//   * A22 -= L21 U12 on the tensor cores (la_rows_update, one call per 64-row block).
+static __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaSmem& sm) {
+    if (T < LA_LU_BLOCKED_MIN) { la_lu_factor_small(A, piv, T, sm); return; }
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int k0 = 0; k0 < T; k0 += LA_NB) {
+        const int nb = min(LA_NB, T - k0), k1 = k0 + nb;
+        if (tid < 32) {
+            for (int j = 0; j < nb; ++j) {
+                const int col = k0 + j;
+                double best = -1.0; int bi = col;
+                for (int i = col + lane; i < T; i += 32) {
+                    const double v = fabs(A[(int64_t)i * T + col]);
+                    if (v > best) { best = v; bi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                if (lane == 0) { piv[col] = bi; sm.ipiv[j] = bi; }
+                if (bi != col && lane < nb) {       // swap inside the panel only; the rest of the rows follows below
+                    double* ra = A + (int64_t)col * T + k0 + lane;
+                    double* rb = A + (int64_t)bi * T + k0 + lane;
+                    const double t = *ra; *ra = *rb; *rb = t;
+                }
+                __syncwarp();
+                const double inv = 1.0 / A[(int64_t)col * T + col];
+                for (int i = col + 1 + lane; i < T; i += 32) {
+                    double* row = A + (int64_t)i * T;
+                    const double l = row[col] * inv;
+                    row[col] = l;
+                    for (int c = col + 1; c < k1; ++c) row[c] -= l * A[(int64_t)col * T + c];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // row interchanges outside the panel, then the unit-lower 16 x 16 block for the U12 solve
+        for (int c = tid; c < T; c += LA_THREADS) {
+            if (c >= k0 && c < k1) continue;
+            for (int j = 0; j < nb; ++j) {
+                const int p = sm.ipiv[j];
+                if (p != k0 + j) {
+                    const double t = A[(int64_t)(k0 + j) * T + c];
+                    A[(int64_t)(k0 + j) * T + c] = A[(int64_t)p * T + c];
+                    A[(int64_t)p * T + c] = t;
+                }
+            }
+        }
+        for (int idx = tid; idx < nb * nb; idx += LA_THREADS)
+            sm.Dk[(idx / nb) * (LA_NB + 1) + idx % nb] = A[(int64_t)(k0 + idx / nb) * T + k0 + idx % nb];
+        __syncthreads();
+        if (k1 < T) {
+            for (int c = k1 + tid; c < T; c += LA_THREADS) {
+                double x[LA_NB];
+#pragma unroll
+                for (int i = 0; i < LA_NB; ++i) {
+                    if (i < nb) {
+                        double v = A[(int64_t)(k0 + i) * T + c];
+                        for (int p = 0; p < i; ++p) v -= sm.Dk[i * (LA_NB + 1) + p] * x[p];
+                        x[i] = v;
+                        A[(int64_t)(k0 + i) * T + c] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int r0 = k1; r0 < T; r0 += 64)
+                la_rows_update(A, A, 0, A, T, r0, min(T, r0 + 64), k0, k1, -1.0, sm, k1);
+        }
+    }
+}
 // B <- A^{-1} B using the factorization above (B: T x T, in place)
 static __device__ __noinline__ void la_lu_solve(const double* __restrict__ LU, const int* __restrict__ piv, double* B, int T, LaSmem& sm) {
     const int tid = threadIdx.x;
@@ -347,19 +493,24 @@ static __device__ __noinline__ void la_lu_solve(const double* __restrict__ LU, c
             }
         __syncthreads();
     }
+    if (T >= LA_LU_BLOCKED_MIN) {
+        la_trsm_blocked(LU, B, T, 2, sm);     // unit lower
+        la_trsm_blocked(LU, B, T, 3, sm);     // upper
+    } else {
     // forward (unit lower) and backward (upper): one thread per column, rows streamed
-    for (int c = tid; c < T; c += LA_THREADS) {
-        for (int i = 1; i < T; ++i) {
-            double v = B[(int64_t)i * T + c];
-            const double* lr = LU + (int64_t)i * T;
-            for (int k = 0; k < i; ++k) v -= lr[k] * B[(int64_t)k * T + c];
-            B[(int64_t)i * T + c] = v;
-        }
-        for (int i = T - 1; i >= 0; --i) {
-            double v = B[(int64_t)i * T + c];
-            const double* ur = LU + (int64_t)i * T;
-            for (int k = i + 1; k < T; ++k) v -= ur[k] * B[(int64_t)k * T + c];
-            B[(int64_t)i * T + c] = v / ur[i];
+        for (int c = tid; c < T; c += LA_THREADS) {
+            for (int i = 1; i < T; ++i) {
+                double v = B[(int64_t)i * T + c];
+                const double* lr = LU + (int64_t)i * T;
+                for (int k = 0; k < i; ++k) v -= lr[k] * B[(int64_t)k * T + c];
+                B[(int64_t)i * T + c] = v;
+            }
+            for (int i = T - 1; i >= 0; --i) {
+                double v = B[(int64_t)i * T + c];
+                const double* ur = LU + (int64_t)i * T;
+                for (int k = i + 1; k < T; ++k) v -= ur[k] * B[(int64_t)k * T + c];
+                B[(int64_t)i * T + c] = v / ur[i];
+            }
         }
     }
     __syncthreads();
