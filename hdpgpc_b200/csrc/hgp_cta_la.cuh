@@ -90,6 +90,35 @@ static __device__ __noinline__ void la_gemm(double* C, const double* A, int tA, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
     const int nt = (T + 63) / 64;
+    // The next K chunk is fetched from global memory (L2) into registers while the tensor cores work on the current
+    // one: a single CTA has nothing else to hide the ~700-cycle load latency behind.
+    double pa[4], pb[4];
+    auto fetch = [&](int r0, int c0, int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = tid + u * LA_THREADS;
+            int r, k;
+            if (tA) { k = idx / 64; r = idx % 64; } else { r = idx / 16; k = idx % 16; }
+            const int gr = r0 + r, gk = k0 + k;
+            pa[u] = (gr < T && gk < T) ? (tA ? A[(int64_t)gk * T + gr] : A[(int64_t)gr * T + gk]) : 0.0;
+            int kb, c;
+            if (tB) { c = idx / 16; kb = idx % 16; } else { kb = idx / 64; c = idx % 64; }
+            const int gkb = k0 + kb, gc = c0 + c;
+            pb[u] = (gkb < T && gc < T) ? (tB ? B[(int64_t)gc * T + gkb] : B[(int64_t)gkb * T + gc]) : 0.0;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = tid + u * LA_THREADS;
+            int r, k;
+            if (tA) { k = idx / 64; r = idx % 64; } else { r = idx / 16; k = idx % 16; }
+            sm.As[r * 20 + k] = pa[u];
+            int kb, c;
+            if (tB) { c = idx / 16; kb = idx % 16; } else { kb = idx / 64; c = idx % 64; }
+            sm.Bs[kb * 72 + c] = pb[u];
+        }
+    };
     for (int tile = 0; tile < nt * nt; ++tile) {
         const int r0 = (tile / nt) * 64, c0 = (tile % nt) * 64;
         double acc[2][4][2];
@@ -97,24 +126,11 @@ static __device__ __noinline__ void la_gemm(double* C, const double* A, int tA, 
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        fetch(r0, c0, 0);
         for (int k0 = 0; k0 < T; k0 += 16) {
-            for (int idx = tid; idx < 64 * 16; idx += LA_THREADS) {
-                int r, k;
-                if (tA) { k = idx / 64; r = idx % 64; } else { r = idx / 16; k = idx % 16; }
-                const int gr = r0 + r, gk = k0 + k;
-                double v = 0.0;
-                if (gr < T && gk < T) v = tA ? A[(int64_t)gk * T + gr] : A[(int64_t)gr * T + gk];
-                sm.As[r * 20 + k] = v;
-            }
-            for (int idx = tid; idx < 16 * 64; idx += LA_THREADS) {
-                int k, c;
-                if (tB) { c = idx / 16; k = idx % 16; } else { k = idx / 64; c = idx % 64; }
-                const int gk = k0 + k, gc = c0 + c;
-                double v = 0.0;
-                if (gk < T && gc < T) v = tB ? B[(int64_t)gc * T + gk] : B[(int64_t)gk * T + gc];
-                sm.Bs[k * 72 + c] = v;
-            }
+            stash();
             __syncthreads();
+            if (k0 + 16 < T) fetch(r0, c0, k0 + 16);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 double a[2], bf[4];
