@@ -424,6 +424,95 @@ def warp_scenario():
     print(f"warp_rec102_T90 -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
+    """Seam trace of a WHOLE offline fit: every chain replay (GPI_model.full_pass_weighted on an empty model) and every
+    HMM smoothing block (forward -> backward -> coupled_state_coef -> _safe_exp) the reference's VI driver
+    (GPI_HDP.include_batch, births / reallocations / accept-reject included) executes, with inputs and outputs.
+    Replaying the trace through the device path and finding every output reproduced means every number the driver's
+    decisions are taken on is reproduced, hence the same cluster assignments and cluster count."""
+    data, labels = load_record(rec, n, leads, stride)
+    sw, x_trains, x_basis, hyper = make_model(data, n_explore_steps=n_explore_steps)
+    GM = hdp.GPI_model.GPI_model if hasattr(hdp, "GPI_model") and hasattr(hdp.GPI_model, "GPI_model") else None
+    import hdpgpc.GPI_model as gm_mod
+    GMc = gm_mod.GPI_model
+    chains, hmms = [], []
+    skipped = [0]
+    orig_fpw = GMc.full_pass_weighted
+    orig_fwd, orig_bwd, orig_csc = sw.forward, sw.backward, sw.coupled_state_coef
+
+    def fpw(self, x_tr, y_tr, resp, *a, **k):
+        fresh = (self.N == 0)
+        fitted_before = bool(self.fitted)
+        out = orig_fpw(self, x_tr, y_tr, resp, *a, **k)
+        r = npy(resp)
+        if fresh and np.count_nonzero(r > 0.99) > 0 and out[0] is not None:
+            kp = self.gp.kernel.get_params()
+            ld = int(np.argmin([float(torch.sum(torch.abs(y_tr[:, :, 0] - torch.from_numpy(data[:, :, l])))) for l in range(data.shape[2])]))
+            chains.append(dict(resp=(r > 0.99), lead=ld, fitted_before=fitted_before,
+                               kernel=np.array([kp["k1__k1__constant_value"], kp["k1__k2__length_scale"], kp["k2__noise_level"]]),
+                               sigma0=float(self.Sigma[0][0, 0]), gamma0=float(self.Gamma[0][0, 0]),
+                               q=npy(out[0]), q_lat=npy(out[1]), n_states=len(self.f_star),
+                               f_last=npy(self.f_star_sm[-1]).reshape(-1),
+                               Sig_chk=np.array([float(torch.trace(self.Sigma[-1])), float(torch.linalg.norm(self.Sigma[-1]))])))
+        else:
+            skipped[0] += 1
+        return out
+
+    cur = {}
+
+    def fwd(pi, trans_A, q):
+        alpha, marg = orig_fwd(pi, trans_A, q)
+        cur.clear()
+        cur.update(pi=npy(pi).copy(), q=npy(q).copy(), transTheta=npy(sw.transTheta).copy(), alpha=npy(alpha).copy())
+        return alpha, marg
+
+    def bwd(trans_A, q, margprob):
+        beta = orig_bwd(trans_A, q, margprob)
+        if "q" in cur and cur["q"].shape == tuple(q.shape) and np.array_equal(cur["q"], npy(q)):
+            cur["beta"] = npy(beta).copy()
+        return beta
+
+    def csc(alpha, beta, trans_A, q, margprobs):
+        out = orig_csc(alpha, beta, trans_A, q, margprobs)
+        if "beta" in cur and np.array_equal(cur["q"], npy(q)):
+            lp = npy(out)
+            rec_ = dict(cur)
+            rec_["z"] = np.argmax(np.log(rec_["alpha"] * rec_["beta"]), axis=1).astype(np.int32)
+            rec_["zpair"] = np.argmax(lp.reshape(lp.shape[0], -1), axis=1).astype(np.int32)
+            hmms.append(rec_)
+            cur.clear()
+        return out
+
+    GMc.full_pass_weighted = fpw
+    sw.forward, sw.backward, sw.coupled_state_coef = fwd, bwd, csc
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            sw.include_batch(x_trains, data)
+    finally:
+        GMc.full_pass_weighted = orig_fpw
+    out = dict(data=data, labels=labels.astype("U1"), x_basis=x_basis, M=np.int64(sw.M),
+               n_chains=np.int64(len(chains)), n_hmm=np.int64(len(hmms)), n_skipped_chain_calls=np.int64(skipped[0]),
+               resp_assigned_last=npy(sw.resp_assigned[-1]).astype(np.int32),
+               train_elbo=np.array([float(e) for e in sw.train_elbo]),
+               free_deg_MNIV=np.float64(sw.free_deg_MNIV),
+               noise_bounds=np.array(sw.kernel_def.k2.noise_level_bounds))
+    for i, c in enumerate(chains):
+        out[f"c{i}_resp"] = np.packbits(c["resp"])
+        out[f"c{i}_meta"] = np.array([c["lead"], c["fitted_before"], c["n_states"], c["sigma0"], c["gamma0"]], dtype=np.float64)
+        for k in ("kernel", "q", "q_lat", "f_last", "Sig_chk"):
+            out[f"c{i}_{k}"] = c[k]
+    for i, h in enumerate(hmms):
+        for k in ("pi", "q", "transTheta", "z", "zpair"):
+            out[f"h{i}_{k}"] = h[k]
+        out[f"h{i}_alpha_last"] = h["alpha"][-1]
+        out[f"h{i}_beta_first"] = h["beta"][0]
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: M={sw.M} chains={len(chains)} (other full_pass calls: {skipped[0]}) hmm blocks={len(hmms)} "
+          f"sizes={np.bincount(out['resp_assigned_last']).tolist()} -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 SCENARIOS = {
     # full state dumps at T=30 (every 3rd sample of the bundled T=90 beats keeps fixtures small)
     "offline_rec100_T30_L1": lambda: offline_scenario("offline_rec100_T30_L1", "100", 40, [0], 3, 24, True),
@@ -434,6 +523,9 @@ SCENARIOS = {
     "inducing_T30": inducing,
     "online_T30": online_extras,
     "warp_rec102_T90": warp_scenario,
+    # seam traces of whole offline fits (every chain replay and HMM block of include_batch)
+    "trace_rec102_T30_L2": lambda: trace_scenario("trace_rec102_T30_L2", "102", 48, [0, 1], 3),
+    "trace_rec100_T90_L1": lambda: trace_scenario("trace_rec100_T90_L1", "100", 40, [0], 1, 5),
 }
 
 if __name__ == "__main__":

@@ -185,3 +185,27 @@ def test_warp_oracle_vs_reference(golden):
         assert np.max(np.abs(xw - z["drv_xw"][:, :, 0, m])) < 1e-10 * np.max(np.abs(z["drv_xw"][:, :, 0, m]))
         assert np.max(np.abs(yw - z["drv_yw"][:, :, 0, m])) < 1e-10 * np.max(np.abs(z["drv_yw"][:, :, 0, m]))
         assert rel(lik, z["drv_liks"][:, m, 0]) < 1e-10
+
+
+def test_oracle_replays_offline_fit_trace(golden):
+    """The seam trace of a whole reference fit (tests/golden/generate_golden.py: trace_scenario): the oracle's chain
+    replay and HMM blocks against what the reference's driver saw (every 3rd chain, every HMM block)."""
+    z = golden("trace_rec102_T30_L2")
+    Y = z["data"]
+    N, T, L = Y.shape
+    for i in range(0, int(z["n_chains"]), 3):
+        resp = np.unpackbits(z[f"c{i}_resp"])[:N].astype(float)
+        lead, fitted_before, n_states, s0, g0 = z[f"c{i}_meta"]
+        kern = tuple(z[f"c{i}_kernel"])
+        og = O.OracleGP(z["x_basis"], kern, float(s0), float(g0), free_deg=int(z["free_deg_MNIV"]))
+        q, ql = og.full_pass_weighted(Y[:, :, int(lead)], resp, fitted_kernel=kern)
+        assert len(og.f_star) == int(n_states)
+        assert rel(q, z[f"c{i}_q"]) < 2e-7
+    for i in range(int(z["n_hmm"])):
+        K = z[f"h{i}_q"].shape[1]
+        pi, PiT, Pi, Pc = O.hmm_operands(z[f"h{i}_transTheta"], z[f"h{i}_pi"], K)
+        qn = z[f"h{i}_q"]
+        alpha, _ = O.hmm_forward(pi, PiT, qn)
+        beta = O.hmm_backward(Pi, qn)
+        assert np.array_equal(O.hard_resp(alpha, beta), z[f"h{i}_z"])
+        assert np.array_equal(O.hard_resp_pair(alpha, beta, Pc, qn), z[f"h{i}_zpair"])
