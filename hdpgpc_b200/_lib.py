@@ -17,6 +17,7 @@ PROTOTYPES = {
     "hgp_last_error": (_c.c_char_p, []),
     "hgp_launch_count": (_i64, []),
     "hgp_pack_leads": (_int, [_p, _i64, _int, _int, _p, _p]),
+    "hgp_pack_leads_slice": (_int, [_p, _i64, _int, _int, _p, _i64, _p]),
     "hgp_chol_batched": (_int, [_p, _i64, _int, _p, _dbl, _p, _p, _p, _p]),
     "hgp_tri_inverse_batched": (_int, [_p, _i64, _int, _p, _p]),
     "hgp_packed_factor_bytes": (_i64, [_int]),

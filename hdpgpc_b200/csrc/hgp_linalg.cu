@@ -11,14 +11,15 @@ namespace {
 constexpr int NB = 16;           // panel width
 constexpr int CHOL_THREADS = 256;
 
-__global__ void pack_leads_kernel(const double* __restrict__ Y, int64_t N, int T, int L, double* __restrict__ out) {
+__global__ void pack_leads_kernel(const double* __restrict__ Y, int64_t N, int T, int L, double* __restrict__ out,
+                                  int64_t plane_stride) {
     int64_t total = N * (int64_t)T * L;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        // i indexes the output [L][N][T]
+        // i indexes the output [L][N][T] (planes plane_stride doubles apart)
         int64_t t = i % T;
         int64_t n = (i / T) % N;
         int64_t ld = i / ((int64_t)T * N);
-        out[i] = Y[(n * T + t) * L + ld];
+        out[ld * plane_stride + n * T + t] = Y[(n * T + t) * L + ld];
     }
 }
 
@@ -236,8 +237,19 @@ extern "C" int hgp_pack_leads(const double* Y_ntl, int64_t N, int T, int L, doub
     if (N == 0) return 0;
     int64_t total = N * (int64_t)T * L;
     int blocks = (int)hgp_min64((total + 255) / 256, 148 * 16);
-    pack_leads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y_ntl, N, T, L, Y_lnt);
+    pack_leads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y_ntl, N, T, L, Y_lnt, N * (int64_t)T);
     HGP_LAUNCH_CHECK("hgp_pack_leads");
+    return 0;
+}
+
+extern "C" int hgp_pack_leads_slice(const double* Y_ntl, int64_t n, int T, int L, double* Y_lnt_at_slice,
+                                    int64_t plane_stride, void* stream) {
+    HGP_REQUIRE(n >= 0 && T > 0 && L > 0 && plane_stride >= n * (int64_t)T, "hgp_pack_leads_slice: bad sizes");
+    if (n == 0) return 0;
+    int64_t total = n * (int64_t)T * L;
+    int blocks = (int)hgp_min64((total + 255) / 256, 148 * 16);
+    pack_leads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y_ntl, n, T, L, Y_lnt_at_slice, plane_stride);
+    HGP_LAUNCH_CHECK("hgp_pack_leads_slice");
     return 0;
 }
 

@@ -137,6 +137,21 @@ class LeadTables:
     def snr(self, out):
         return ops.snr_states(self.Y, self.mu_sm, self.snr_state_of, out=out)
 
+    def score_slice(self, n0, n1, out, snr_out=None):
+        """Tile-path scores (and SNR) of beats [n0, n1) only; n0 must be a multiple of the 64-beat tile.  The exception
+        pairs (score_exceptions) need the whole plane and run once all slices are in."""
+        if not self.use_tiles or n0 % 64:
+            raise HgpError("score_slice needs the tile path and a tile-aligned slice start")
+        fuse = snr_out is not None and self.snr_state_of is not None
+        ops.score_tiles(self.Y[n0:n1], self.nu, self.Wpacked, self.state_of[n0:n1], self.factor_of_cluster,
+                        out=out[n0:n1], tile_state=self.tile_state[n0 // 64:],
+                        mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of[n0:n1] if fuse else None,
+                        snr_out=snr_out[n0:n1] if fuse else None)
+
+    def score_exceptions(self, out):
+        if self.use_tiles and self.pair_n is not None:
+            ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m, out=out)
+
 
 def sharded_hmm_exchange(smooth, K, rank, world, group, device):
     """Exact HMM smoothing over rank-sharded beats.  Every rank scans its slice from
@@ -241,6 +256,45 @@ class EStepEngine:
         if self.world > 1:
             torch.distributed.all_reduce(packed, group=self.group)
         return dict(Nm=Nm, transStateCount=trans, startStateCount=start, Q_em=Qem, packed=packed)
+
+    def sweep_from_host(self, Y_host, n_slices=8):
+        """The end-to-end public call: beats arrive in host memory (pinned for an asynchronous copy) in the reference's
+        [N, T, L] layout (tests/test_offline.py:31), labels and statistics go back to the host.  The beats are cut into
+        tile-aligned slices; the host-to-device copy of slice k+1 runs on a copy stream under the scoring of slice k."""
+        N, L, T = self.N, self.L, self.leads[0].T
+        if tuple(Y_host.shape) != (N, T, L):
+            raise HgpError(f"sweep_from_host: expected beats of shape {(N, T, L)}, got {tuple(Y_host.shape)}")
+        if not all(tb.use_tiles for tb in self.leads):
+            raise HgpError("sweep_from_host needs the tile path (shared covariance per cluster, T <= 256)")
+        dev = self.device
+        if getattr(self, "_stage", None) is None:
+            self._stage = torch.empty((N, T, L), dtype=F64, device=dev)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._Yp = torch.empty((L, N, T), dtype=F64, device=dev)
+        for ld, tb in enumerate(self.leads):
+            tb.Y = self._Yp[ld]
+        per = max(64, -(-N // (n_slices * 64)) * 64)
+        bounds = [(n0, min(N, n0 + per)) for n0 in range(0, N, per)]
+        main = torch.cuda.current_stream()
+        self._copy_stream.wait_stream(main)          # earlier sweeps are done with the staging buffer
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for n0, n1 in bounds:
+                self._stage[n0:n1].copy_(Y_host[n0:n1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        for (n0, n1), ev in zip(bounds, events):
+            main.wait_event(ev)
+            ops.pack_leads_slice(self._stage[n0:n1], self._Yp, n0)
+            for ld, tb in enumerate(self.leads):
+                tb.score_slice(n0, n1, self.q[ld], self.snr[ld] if self.use_snr else None)
+        for ld, tb in enumerate(self.leads):
+            tb.score_exceptions(self.q[ld])
+        qbar, e, w, hm = self.responsibilities()
+        st = self.statistics(qbar, hm)
+        st.update(z_host=hm.z.cpu(), stats_host=st["packed"].cpu(), z=hm.z, zpair=hm.zpair)
+        return st
 
     def sweep(self):
         self.score_all()

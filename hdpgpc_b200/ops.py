@@ -38,6 +38,18 @@ def pack_leads(Y_ntl):
     return out
 
 
+def pack_leads_slice(Y_ntl_slice, Yp, n0):
+    """[n, T, L] slice (device) -> rows [n0, n0 + n) of every plane of Yp[L, N, T]."""
+    lib = _lib_ready()
+    Ys = _dev(Y_ntl_slice).contiguous()
+    n, T, L = Ys.shape
+    Lp, N, Tp = Yp.shape
+    if (Lp, Tp) != (L, T) or n0 + n > N or not Yp.is_contiguous():
+        raise _lib.HgpError("pack_leads_slice: shape mismatch")
+    dst = Yp.data_ptr() + n0 * T * 8
+    check(lib.hgp_pack_leads_slice(ptr(Ys), n, T, L, ctypes.c_void_p(dst), N * T, stream_ptr()), "hgp_pack_leads_slice")
+
+
 def chol_batched(Sigma, add_diag=None, jitter_scale=1e-8, want_logdet=False):
     """GPI_model._chol_spd for a stack [F, T, T].  Returns (L, info[, logdet])."""
     lib = _lib_ready()

@@ -43,6 +43,11 @@ int64_t hgp_launch_count(void);
  * y_trains[:, :, [ld]] at GPI_HDP.py:2901, :2985).  Kernels want one contiguous [N, T] plane
  * per lead: Yp[L, N, T]. */
 int hgp_pack_leads(const double* Y_ntl, int64_t N, int T, int L, double* Y_lnt, void* stream);
+/* The same for a slice of n beats that has just arrived from the host: Y_ntl points at the slice, Y_lnt_at_slice at the
+ * slice's first beat inside plane 0 of the full Yp[L, N, T] (plane_stride = N * T doubles).  Lets the host-to-device
+ * copy of the next slice overlap the scoring of this one (EStepEngine.sweep_from_host). */
+int hgp_pack_leads_slice(const double* Y_ntl, int64_t n, int T, int L, double* Y_lnt_at_slice, int64_t plane_stride,
+                         void* stream);
 
 /* ---- SPD factorisation: GPI_model._chol_spd (GPI_model.py:83-87) -------------------------
  * For f in [0, F):  M = Sigma[f] + add_diag[f] * I   (add_diag may be NULL; the `first` rule

@@ -667,6 +667,23 @@ def test_sharded_hmm_emulated_ranks_bitwise():
     assert torch.equal(warm.zpair, cold.zpair) and torch.equal(warm.boundary_out, cold.boundary_out)
 
 
+def test_sweep_from_host_equals_resident_sweep():
+    """The end-to-end call (pinned host beats, sliced H2D copies overlapped with scoring) gives bitwise the same scores,
+    labels and statistics as the device-resident sweep, for a beat count that is not a multiple of the slice size."""
+    from hdpgpc_b200 import synthetic
+    N, T, L, M = 1000, 64, 2, 5
+    wl = synthetic.make_workload(N, T=T, L=L, M=M, seed=21, device="cuda")
+    eng = synthetic.build_engine(wl)
+    ref = eng.sweep()
+    q_ref = eng.q.clone()
+    z_ref, packed_ref = ref["z"].clone(), ref["packed"].clone()
+    Y_host = wl["Y"].cpu().pin_memory()
+    eng.q.zero_()
+    out = eng.sweep_from_host(Y_host, n_slices=3)
+    assert torch.equal(eng.q, q_ref)
+    assert torch.equal(out["z_host"], z_ref.cpu()) and torch.equal(out["stats_host"], packed_ref.cpu())
+
+
 # ---------------------------------------------------------------------------------------------
 # seam trace of a whole offline fit
 # ---------------------------------------------------------------------------------------------
