@@ -92,7 +92,7 @@ __host__ __device__ inline TileSmem tile_smem_layout(int nrb) {
     s.wst = nrb * Y_CHUNK_DOUBLES * 8;
     s.red = s.wst + STAGES * W_STAGE_BYTES;
     s.bars = s.red + 2 * NCW * BT * 8 + BT * 4;      // + the tile's state indices (mixed-state epilogue)
-    s.total = s.bars + 2 * STAGES * 8;
+    s.total = s.bars + (2 * STAGES + 4) * 8;     // full/empty per stage + epilogue full/free per reduction buffer
     return s;
 }
 
@@ -177,6 +177,8 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
     double* red = reinterpret_cast<double*>(smem_raw + lay.red);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
     uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* epi_full = empty_bar + STAGES;     // [2]: all consumer warps have written their partial |z|^2
+    uint64_t* epi_free = epi_full + 2;           // [2]: the reducer warp is done with the buffer
 
     const int tid = threadIdx.x;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the role / row-block branches
@@ -187,6 +189,10 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);         // the producer's arrive.expect_tx; the bulk copies complete the bytes
             mbar_init(&empty_bar[s], NCW);      // one arrive per consumer warp
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&epi_full[b], NCW);
+            mbar_init(&epi_free[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -224,6 +230,29 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                     }
                 }
             }
+            if (warp == NCW + 1) {
+                // Reducer: the consumers never meet at a CTA barrier for the per-beat sum over the eight warps' partial
+                // |z|^2 -- they drop their partials into a double-buffered array, arrive on an mbarrier and move on to
+                // the next cluster; this (otherwise idle, register-donating) warp adds them up in a fixed order and
+                // writes the scores.  Without the barrier the two consumer warps of a sub-partition are free to drift
+                // apart, so their epilogues stop coinciding and the tensor pipe keeps working through them.
+                const int64_t n0 = tile * BT;
+                for (int m = m_begin; m < m_end; ++m, ++it) {
+                    const int b = it & 1;
+                    const int64_t na = n0 + lane, nb = na + 32;
+                    const int sa = (na < N) ? state_of[na * M + m] : -1;
+                    const int sb = (nb < N) ? state_of[nb * M + m] : -1;
+                    mbar_wait(&epi_full[b], (it >> 1) & 1);
+                    const double* rbuf = red + b * (NCW * BT);
+                    double ra = 0.0, rb = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NCW; ++w) { ra += rbuf[w * BT + lane]; rb += rbuf[w * BT + lane + 32]; }
+                    if (na < N) q[na * M + m] = (sa >= 0) ? (-0.5 * ra - half_T_log2pi) : 0.0;
+                    if (nb < N) q[nb * M + m] = (sb >= 0) ? (-0.5 * rb - half_T_log2pi) : 0.0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&epi_free[b]);
+                }
+            }
             __syncthreads();   // consumers are done with this item; the beat tile may be rewritten
         }
     } else {
@@ -255,7 +284,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                     nu_r[j] = (st_u >= 0 && row < T) ? __ldg(nu + (int64_t)st_u * T + row) : 0.0;
                 }
                 int st_epi = -1;
-                if (tid < BT && n0 + tid < N) st_epi = state_of[(n0 + tid) * M + m];
+                if (st_u == -2 && tid < BT && n0 + tid < N) st_epi = state_of[(n0 + tid) * M + m];   // mixed-state epilogue only
 
                 if (nrb == MAX_NRB) {
                     // T = 256 fast path.  This warp's row blocks are rb_0 = w < rb_1 = 15-w < rb_2 = 16+w < rb_3 = 31-w;
@@ -312,7 +341,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                 }
                 // ---- epilogue: z = acc - nu, |z|^2 per beat ----
                 double* rbuf = red + (epi & 1) * (NCW * BT);
-                ++epi;
+                mbar_wait(&epi_free[epi & 1], ((epi >> 1) & 1) ^ 1);    // the reducer has consumed this buffer's last use
                 if (st_u >= -1) {
                     // every beat of the tile scores against the same state: one nu value per row block
 #pragma unroll
@@ -370,16 +399,9 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                             }
                     }
                 }
-                consumer_bar();
-                if (tid < BT) {
-                    const int64_t n = n0 + tid;
-                    if (n < N) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int w = 0; w < NCW; ++w) s += rbuf[w * BT + tid];
-                        q[n * M + m] = (st_epi >= 0) ? (-0.5 * s - half_T_log2pi) : 0.0;
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&epi_full[epi & 1]);
+                ++epi;
             }
             __syncthreads();   // matches the producer's end-of-item barrier
         }
@@ -530,20 +552,52 @@ snr_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* _
             int s_cur = -2;
             double v[NREG], sig = 0.0;
             double my_sig = 0.0, my_noi = 0.0;       // lane b keeps the sums of beat b: one log10 per lane, not per beat
-            for (int b = 0; b < nb; ++b) {
-                const int s = __shfl_sync(0xffffffffu, my_s, b);
-                if (s != s_cur) {
-                    s_cur = s;
-                    const double* r = mu_sm + (int64_t)max(s, 0) * T;
-                    double p = 0.0;
+            auto reload = [&](int s) {
+                s_cur = s;
+                const double* r = mu_sm + (int64_t)max(s, 0) * T;
+                double p = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NREG; ++k) {
-                        const int t = lane + 32 * k;
-                        v[k] = (s >= 0 && t < T) ? __ldg(r + t) : 0.0;
-                        p += v[k] * v[k];
-                    }
-                    sig = warp_sum(p);
+                for (int k = 0; k < NREG; ++k) {
+                    const int t = lane + 32 * k;
+                    v[k] = (s >= 0 && t < T) ? __ldg(r + t) : 0.0;
+                    p += v[k] * v[k];
                 }
+                sig = warp_sum(p);
+            };
+            int b = 0;
+            while (b < nb) {
+              // four beats per trip while they share the state: four independent reduction chains in flight
+              bool four = false;
+              if (b + 4 <= nb) {
+                const int s0 = __shfl_sync(0xffffffffu, my_s, b), s1 = __shfl_sync(0xffffffffu, my_s, b + 1);
+                const int s2 = __shfl_sync(0xffffffffu, my_s, b + 2), s3 = __shfl_sync(0xffffffffu, my_s, b + 3);
+                four = (s0 == s1 && s0 == s2 && s0 == s3);
+                if (four && s0 != s_cur) reload(s0);
+              }
+              if (four) {
+                double n0_ = 0.0, n1_ = 0.0, n2_ = 0.0, n3_ = 0.0;
+                const double* y = ytile + b * T;
+#pragma unroll
+                for (int k = 0; k < NREG; ++k) {
+                    const int t = lane + 32 * k;
+                    if (t < T) {
+                        const double d0 = v[k] - y[t], d1 = v[k] - y[T + t], d2 = v[k] - y[2 * T + t], d3 = v[k] - y[3 * T + t];
+                        n0_ += d0 * d0; n1_ += d1 * d1; n2_ += d2 * d2; n3_ += d3 * d3;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    n0_ += __shfl_xor_sync(0xffffffffu, n0_, o); n1_ += __shfl_xor_sync(0xffffffffu, n1_, o);
+                    n2_ += __shfl_xor_sync(0xffffffffu, n2_, o); n3_ += __shfl_xor_sync(0xffffffffu, n3_, o);
+                }
+                if (lane >= b && lane < b + 4) {
+                    my_sig = sig;
+                    my_noi = lane == b ? n0_ : lane == b + 1 ? n1_ : lane == b + 2 ? n2_ : n3_;
+                }
+                b += 4;
+              } else {
+                const int s = __shfl_sync(0xffffffffu, my_s, b);
+                if (s != s_cur) reload(s);
                 const double* y = ytile + b * T;
                 double noi = 0.0;
 #pragma unroll
@@ -554,6 +608,8 @@ snr_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* _
                 }
                 noi = warp_sum(noi);
                 if (lane == b) { my_sig = sig; my_noi = noi; }
+                ++b;
+              }
             }
             if (lane < nb)
                 snr[(n0 + lane) * M + m] = (my_s >= 0) ? 10.0 * log10((my_sig + HGP_EPS) / (my_noi + HGP_EPS)) : 0.0;
