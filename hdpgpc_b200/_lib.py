@@ -110,4 +110,5 @@ class ChainDesc(ctypes.Structure):
                  ("r_first", _dbl), ("member_beats", _p), ("Y", _p)] +
                 [(n, _p) for n in ("f_star", "f_star_sm", "cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma",
                                    "int_m_mean", "int_m_r_cov", "int_scale", "int_n0",
-                                   "obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0", "work", "piv", "status")])
+                                   "obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0", "work", "piv", "status")] +
+                [("start_members", _int), ("start_params", _int), ("phases", _int), ("reserved_", _int)])

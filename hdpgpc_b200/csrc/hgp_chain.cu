@@ -82,10 +82,11 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
     Mniw mi{d.int_m_mean, d.int_m_r_cov, d.int_scale, d.int_n0};
     Mniw mo{d.obs_m_mean, d.obs_m_r_cov, d.obs_scale, d.obs_n0};
     int fail = 0;
-    int N = 0;          // members assimilated
-    int p = 0;          // index of the last parameter set (A, Gamma, C, Sigma)
+    int N = d.start_members;          // members assimilated
+    int p = d.start_params;           // index of the last parameter set (A, Gamma, C, Sigma)
+    const int phases = d.phases ? d.phases : 15;
     for (int k = 0; k < d.n_members; ++k) {
-        const int s = k;                      // last state index before this member
+        const int s = d.start_members + k;    // last state index before this member
         const double* m = d.f_star_sm + (int64_t)s * T;
         const double* Sg = d.cov_f_sm + s * tt;
         const double* A = d.A + p * tt;
@@ -96,8 +97,9 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
         double* m_new = d.f_star + (int64_t)(s + 1) * T;
         double* S_new = d.cov_f + (s + 1) * tt;
         // ---------------- Kalman update (GPI.py:104-150) ----------------
+        const bool prior = d.first_is_prior && s == 0;
+        if (phases & 1) {
         la_gemv(v0, A, m, T, 0.0, nullptr);                              // v0 = A m  (x_basis_mean)
-        const bool prior = d.first_is_prior && k == 0;
         const double* P;
         if (prior) {
             P = Sg;                                                      // P_t = cov_prior; f* = 0; R = r_first I
@@ -136,9 +138,10 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
         }
         la_copy(d.f_star_sm + (int64_t)(s + 1) * T, m_new, T);
         la_copy(d.cov_f_sm + (s + 1) * tt, S_new, n);
+        }
         N += 1;
         // ---------------- pair smoother (GPI_model.py:705-716, GPI.py:294-299) ----------------
-        if (N > 1) {
+        if ((phases & 2) && N > 1) {
             const double* m0 = d.f_star + (int64_t)s * T;
             const double* S0 = d.cov_f + s * tt;
             la_gemm(W0, A, 0, S0, 0, T, 1.0, 0.0, nullptr, sm);          // A S0
@@ -157,6 +160,7 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
             la_gemm(d.cov_f_sm + s * tt, W0, 0, W6, 1, T, 1.0, 1.0, S0, sm);   // S0 + J (S1 - P) J^T
         }
         // ---------------- MNIW step (GPI_model.py:966-1101) ----------------
+        if (!(phases & 4)) continue;
         const bool below = d.estimation_limit <= 0 || N < d.estimation_limit;
         if (N > 1 && below) {
             // the reference also factorises P = A cov_ A^T + Gamma here and discards it (:990-998); only a
@@ -184,8 +188,12 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
     }
     // ---------------- full RTS pass (GPI_model.py:687-703, GPI.py:262-270) ----------------
     // means = f_star[1:], covars = cov_f[1:], A_prior = A[1:], Gamma_prior = Gamma[1:]
-    const int Tn = d.n_members;
+    const int Tn = d.start_members + d.n_members;
     const int nA = p;      // len(A[1:])
+    if (!(phases & 8)) {
+        if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
+        return;
+    }
     if (Tn >= 1) {
         // the last state is its own smoothed value
         la_copy(d.f_star_sm + (int64_t)Tn * T, d.f_star + (int64_t)Tn * T, T);

@@ -107,6 +107,14 @@ class GPI_model:
                    cov_f_sm=g("cov_f_sm"), cov_f=g("cov_f"), kernel=g("kernel"), device=device)
         if prefix + "A_def" in z:
             self.defaults = {k: _stack(g(k + "_def")[None], self.device)[0] for k in ("A", "Gamma", "C", "Sigma")}
+        if prefix + "int_m_mean" in z:      # MNIW posteriors: needed to continue the chain online
+            for name, pre in (("internal", "int_"), ("observation", "obs_")):
+                st = {k: _stack(g(pre + k)[None], self.device)[0].clone() for k in ("m_mean", "m_r_cov", "scale")}
+                st["n0"] = torch.tensor([float(g(pre + "n0"))], dtype=F64, device=self.device)
+                setattr(self, name, st)
+            self.fitted = bool(g("fitted")) if prefix + "fitted" in z else True
+            self.annealing = bool(z[prefix + "annealing"]) if prefix + "annealing" in z else True
+            self.free_deg = float(z[prefix + "free_deg"]) if prefix + "free_deg" in z else 5.0
         return self
 
     # ---- index rules (host integer work) ----
@@ -428,6 +436,111 @@ class GPI_model:
         mean_, cov_, C_, Sigma_ = self.smoother_weighted(x_train, y, h)
         return self.log_sq_error(x_train, y, mean=mean_[-1], cov=cov_[-1], C=C_[-1], Sigma=Sigma_[-1], i=-1,
                                  first=(len(self.indexes) == 1))
+
+    # ---- online assimilation: the reference's three seam calls, one by one -----------------------------------------
+    _HIST = ("f_star", "f_star_sm", "cov_f", "cov_f_sm")
+    _PAR = ("A", "Gamma", "C", "Sigma")
+
+    def _reserve(self, n_states, n_params):
+        """Make room for n_states states / n_params parameter sets: the histories are views of storage tensors that
+        grow geometrically, so an online append does not copy the chain (reference: Python list append)."""
+        store = getattr(self, "_store", None)
+        if store is None:
+            store = self._store = {}
+        for names, need in ((self._HIST, n_states), (self._PAR, n_params)):
+            for k in names:
+                cur = getattr(self, k)
+                st = store.get(k)
+                shares = st is not None and st.data_ptr() == cur.data_ptr() and st.shape[0] >= cur.shape[0]
+                if not shares or st.shape[0] < need:
+                    cap = max(need, 2 * cur.shape[0], 8)
+                    st = torch.zeros((cap,) + tuple(cur.shape[1:]), dtype=F64, device=self.device)
+                    st[:cur.shape[0]] = cur
+                    store[k] = st
+                    setattr(self, k, st[:cur.shape[0]])
+
+    def _online_desc(self, y_row, phases, start_members):
+        T, dev = self.T, self.device
+        if not hasattr(self, "internal"):
+            raise HgpError("online assimilation needs the MNIW state of the chain (a model built by full_pass_weighted, "
+                           "GPI_model.fresh / unfitted, or from_dump of a full dump)")
+        lib = ops._lib.load()
+        st = self._store
+        c, ell, noise = self.kernel
+        if getattr(self, "_online_work", None) is None:
+            self._online_work = (torch.zeros(int(lib.hgp_chain_work_doubles(T)), dtype=F64, device=dev),
+                                 torch.zeros(T, dtype=torch.int32, device=dev))
+        work, piv = self._online_work
+        return dict(n_members=1, first_is_prior=int(start_members == 0 and getattr(self, "ini_cov_is_prior", False)),
+                    annealing=int(getattr(self, "annealing", True)),
+                    estimation_limit=0 if np.isinf(self.estimation_limit) else int(self.estimation_limit),
+                    r_first=(c + noise) - c, member_beats=torch.zeros(1, dtype=torch.int32, device=dev), Y=y_row,
+                    **{k: st[k] for k in self._HIST + self._PAR},
+                    **{"int_" + k: v for k, v in self.internal.items()}, **{"obs_" + k: v for k, v in self.observation.items()},
+                    work=work, piv=piv, status=torch.zeros(2, dtype=torch.int32, device=dev),
+                    start_members=start_members, start_params=self.A.shape[0] - 1, phases=phases)
+
+    def _init_mniw(self):
+        if not hasattr(self, "internal"):
+            eye = torch.eye(self.T, dtype=F64, device=self.device)
+            n0 = lambda: torch.tensor([getattr(self, "free_deg", 5.0)], dtype=F64, device=self.device)
+            self.internal = dict(m_mean=self.A[0].clone(), m_r_cov=eye.clone(), scale=self.Gamma[0].clone(), n0=n0())
+            self.observation = dict(m_mean=self.C[0].clone(), m_r_cov=eye.clone(), scale=self.Sigma[0].clone(), n0=n0())
+
+    def include_weighted_sample(self, index, x_train, x_warped, y, h, snr=None):
+        """GPI_model.include_weighted_sample (GPI_model.py:353-375) -> include_sample (:325-351) ->
+        IterativeGaussianProcess.posterior (GPI.py:72-151): one Kalman update in Joseph form from the last SMOOTHED state
+        with the last parameter set; the new state is appended to the filtered and smoothed histories.  The first beat
+        of an unfitted model runs the hyper-fit first (:361-365).  Returns x_basis like the reference."""
+        if snr is not None:
+            raise HgpError("include_weighted_sample(snr=...) is not built")
+        if self._off_grid(x_train) is not None:
+            raise HgpError("include_weighted_sample on a grid other than x_basis is not built; no CPU fallback")
+        if h != 1.0:
+            return self.x_basis          # include_sample(posterior=False): nothing is stored (:343-351)
+        Y = self._beats(torch.as_tensor(np.asarray(y.detach().cpu() if isinstance(y, torch.Tensor) else y,
+                                                   dtype=np.float64).reshape(1, -1)))
+        if self.N == 0 and not getattr(self, "fitted", True):
+            self.fit_kernel_params(None, Y[0])
+        self._init_mniw()
+        nF = self.f_star.shape[0]
+        self._reserve(nF + 1, self.A.shape[0] + 1)
+        desc = self._online_desc(Y, 1, self.N)
+        ops.chain_run([desc], self.T)
+        for k in self._HIST:
+            setattr(self, k, self._store[k][:nF + 1])
+        self.indexes.append(int(index))
+        self.N += 1
+        self._last_y = Y
+        self._tables = None
+        return self.x_basis
+
+    def backwards_pair(self, h, snr=None):
+        """GPI_model.backwards_pair (:705-724) -> backward_notrange (GPI.py:272-300): RTS smoothing of the last two
+        states; rewrites f_star_sm[-2:], cov_f_sm[-2:]."""
+        if snr is not None:
+            raise HgpError("backwards_pair(snr=...) is not built")
+        if len(self.indexes) > 1 and h == 1.0:
+            ops.chain_run([self._online_desc(self._last_y, 2, self.N - 1)], self.T)
+            self._tables = None
+
+    def bayesian_new_params(self, h, model_type="dynamic", full_data=False, q=None, force=False, snr=1.0):
+        """GPI_model.bayesian_new_params (:966-1115), 1-step dynamic form: MNIW update of (A, Gamma) from the last two
+        smoothed means and of (C, Sigma) from (y, last smoothed mean) when 1 < N < estimation_limit, then a new
+        parameter set (with the annealing terms) is appended while N < estimation_limit."""
+        if full_data or force or snr != 1.0 or model_type != "dynamic" or h != 1.0:
+            raise HgpError("bayesian_new_params: only the 1-step dynamic update with h = 1 is built")
+        nC = self.A.shape[0]
+        self._reserve(self.f_star.shape[0], nC + 1)
+        desc = self._online_desc(self._last_y, 4, self.N - 1)
+        ops.chain_run([desc], self.T)
+        fail, n_par = (int(v) for v in desc["status"])
+        if fail:
+            # the reference keeps the previous parameters and prints (GPI_model.py:1068-1071); the kernel already did
+            pass
+        for k in self._PAR:
+            setattr(self, k, self._store[k][:n_par])
+        self._tables = None
 
     # ---- chain replay -------------------------------------------------------------------------------
     @classmethod

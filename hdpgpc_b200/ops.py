@@ -299,7 +299,7 @@ def chain_run(descs, T):
     keep = []
     for i, d in enumerate(descs):
         for name, _ty in _lib.ChainDesc._fields_:
-            v = d[name]
+            v = d.get(name, 0)
             if isinstance(v, torch.Tensor):
                 keep.append(v)
                 v = v.data_ptr()

@@ -187,13 +187,20 @@ typedef struct hgp_chain_desc {
     double r_first;           /* (c + noise) - c of the fitted kernel (kernel(x) - kernel(x, x), GPI.py:139) */
     const int* member_beats;  /* [n_members] row of Y per member */
     const double* Y;          /* beats plane [N][T] */
-    double *f_star, *f_star_sm;                 /* [n_members + 1][T] */
-    double *cov_f, *cov_f_sm, *A, *Gamma, *C, *Sigma;   /* [n_members + 1][T][T] */
+    double *f_star, *f_star_sm;                 /* [start_members + n_members + 1][T] */
+    double *cov_f, *cov_f_sm, *A, *Gamma, *C, *Sigma;   /* [start_members + n_members + 1][T][T] */
     double *int_m_mean, *int_m_r_cov, *int_scale, *int_n0;   /* MNIW over (A, Gamma): in/out; n0 is a device scalar */
     double *obs_m_mean, *obs_m_r_cov, *obs_scale, *obs_n0;   /* MNIW over (C, Sigma) */
     double* work;             /* >= hgp_chain_work_doubles(T) */
     int* piv;                 /* >= T */
     int* status;              /* [2] out: first member (1-based) whose MNIW factorization failed or 0; parameter sets written */
+    /* Online use: continue an existing chain and / or run only some of the per-member phases, so that the reference's
+     * three seam calls GPI_model.include_weighted_sample (:353-375), backwards_pair (:705-724) and bayesian_new_params
+     * (:966-1115) can be issued one by one (GPI_HDP.include_sample, GPI_HDP.py:2187-2192). */
+    int start_members;        /* members already held by the histories before member 0 of this call (0: fresh chain) */
+    int start_params;         /* index of the last parameter set (A, Gamma, C, Sigma) already written (0: fresh chain) */
+    int phases;               /* bit 0 Kalman update, bit 1 pair smoother, bit 2 MNIW step, bit 3 full RTS pass; 0 = all */
+    int reserved_;
 } hgp_chain_desc;
 int64_t hgp_chain_desc_bytes(void);
 int64_t hgp_chain_work_doubles(int T);

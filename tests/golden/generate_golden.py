@@ -513,6 +513,53 @@ def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
           f"sizes={np.bincount(out['resp_assigned_last']).tolist()} -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def online_steps():
+    """The three seam methods of one online assimilation, called one by one on an existing chain
+    (GPI_HDP.include_sample, GPI_HDP.py:2187-2192): GPI_model.include_weighted_sample (:353-375), backwards_pair
+    (:705-724), bayesian_new_params (:966-1115); and the seeding of a fresh model with one beat (:1289-1297)."""
+    data, _ = load_record("100", 30, [0], 3)
+    N, T, L = data.shape
+    sw, x_trains, x_basis, hyper = make_model(data)
+    out = dict(data=data, x_basis=x_basis)
+    xt = torch.from_numpy(x_trains)
+    yt = torch.from_numpy(data)
+    xb = torch.from_numpy(x_basis)
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp = sw.create_gp_default()
+        resp = torch.zeros(N)
+        resp[[0, 2, 3, 5, 8, 9, 13, 14, 20]] = 1.0
+        gp.full_pass_weighted(xt, yt[:, :, [0]], resp)
+        dump_gp(gp, "pre_", out, full=True)
+        out["pre_annealing"] = np.bool_(gp.annealing)
+        out["pre_free_deg"] = np.float64(gp.free_deg_MNIV)
+        beats = [22, 25, 27]
+        out["beats"] = np.array(beats)
+        for k, n in enumerate(beats):
+            gp.include_weighted_sample(n, xb, xb, yt[n, :, [0]], 1.0)
+            out[f"s{k}_inc_f"] = npy(gp.f_star[-1]); out[f"s{k}_inc_cov"] = npy(gp.cov_f[-1])
+            gp.backwards_pair(1.0)
+            out[f"s{k}_pair_f"] = stack(gp.f_star_sm[-2:]); out[f"s{k}_pair_cov"] = stack(gp.cov_f_sm[-2:])
+            gp.bayesian_new_params(1.0)
+            for nm in ("A", "Gamma", "C", "Sigma"):
+                out[f"s{k}_{nm}"] = npy(getattr(gp, nm)[-1])
+            out[f"s{k}_n0"] = np.array([gp.internal_params.n0, gp.observation_params.n0], dtype=np.float64)
+            out[f"s{k}_lenA"] = np.int64(len(gp.A))
+        dump_gp(gp, "post_", out, full=True)
+        out["post_q"] = npy(gp.compute_sq_err_all(xt, yt[:, :, [0]]))
+        out["post_q_lat"] = npy(gp.compute_q_lat_all(xt))
+        # seeding a fresh model with its representative beat (q_simple, GPI_HDP.py:1289-1297)
+        seed = sw.create_gp_default()
+        seed.include_weighted_sample(0, xb, xb, yt[4, :, [0]], 1.0)
+        dump_gp(seed, "seed_", out, full=True)
+        out["seed_q"] = npy(seed.compute_sq_err_all(xt, yt[:, :, [0]]))
+    out["noise_bounds"] = np.array(sw.kernel_def.k2.noise_level_bounds)
+    out["ini_sigma_def"] = np.float64(sw.ini_sigma_def)
+    out["ini_gamma_def"] = np.float64(sw.ini_gamma_def)
+    path = os.path.join(HERE, "online_steps_T30.npz")
+    np.savez_compressed(path, **out)
+    print(f"online_steps_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 SCENARIOS = {
     # full state dumps at T=30 (every 3rd sample of the bundled T=90 beats keeps fixtures small)
     "offline_rec100_T30_L1": lambda: offline_scenario("offline_rec100_T30_L1", "100", 40, [0], 3, 24, True),
@@ -523,6 +570,7 @@ SCENARIOS = {
     "inducing_T30": inducing,
     "online_T30": online_extras,
     "warp_rec102_T90": warp_scenario,
+    "online_steps_T30": online_steps,
     # seam traces of whole offline fits (every chain replay and HMM block of include_batch)
     "trace_rec102_T30_L2": lambda: trace_scenario("trace_rec102_T30_L2", "102", 48, [0, 1], 3),
     "trace_rec100_T90_L1": lambda: trace_scenario("trace_rec100_T90_L1", "100", 40, [0], 1, 5),

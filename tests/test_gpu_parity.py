@@ -416,6 +416,49 @@ def test_hyperfit_vs_oracle(golden):
         assert abs(out[k, 0] - s) < TOL * s and abs(out[k, 1] - ell) < TOL * ell and abs(out[k, 2] - noise) < TOL * noise
 
 
+def test_online_seam_steps_vs_reference(golden):
+    """One online assimilation as the reference issues it (GPI_HDP.include_sample, GPI_HDP.py:2187-2192): the three seam
+    calls include_weighted_sample / backwards_pair / bayesian_new_params one by one on an existing chain (SURVEY 8a rows
+    a6, a7, a8), three beats in a row, then the scores of the grown chain; and the seeding of a fresh model with one
+    beat (q_simple, GPI_HDP.py:1289-1297)."""
+    import hdpgpc_b200 as hb
+    z = golden("online_steps_T30")
+    Y = z["data"][:, :, 0]
+    gp = hb.GPI_model.from_dump(z, "pre_")
+    close = lambda a, ref: np.max(np.abs(a.cpu().numpy().reshape(ref.shape) - ref)) < 1e-8 * np.max(np.abs(ref))
+    for k, n in enumerate(z["beats"]):
+        gp.include_weighted_sample(int(n), None, None, Y[n], 1.0)
+        assert gp.N == 10 + k and gp.indexes[-1] == int(n)
+        assert close(gp.f_star[-1], z[f"s{k}_inc_f"]) and close(gp.cov_f[-1], z[f"s{k}_inc_cov"])
+        assert torch.equal(gp.f_star_sm[-1], gp.f_star[-1])
+        gp.backwards_pair(1.0)
+        assert close(gp.f_star_sm[-2:], z[f"s{k}_pair_f"]) and close(gp.cov_f_sm[-2:], z[f"s{k}_pair_cov"])
+        gp.bayesian_new_params(1.0)
+        assert gp.A.shape[0] == int(z[f"s{k}_lenA"])
+        for nm in ("A", "Gamma", "C", "Sigma"):
+            assert close(getattr(gp, nm)[-1], z[f"s{k}_{nm}"]), (k, nm)
+        assert float(gp.internal["n0"]) == z[f"s{k}_n0"][0] and float(gp.observation["n0"]) == z[f"s{k}_n0"][1]
+    for nm in ("f_star", "f_star_sm"):
+        assert close(getattr(gp, nm), z["post_" + nm])
+    for nm in ("cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma"):
+        assert close(getattr(gp, nm), z["post_" + nm]), nm
+    assert rel(gp.compute_sq_err_all(None, Y[:, :, None]), z["post_q"]) < TOL
+    ql = gp.compute_q_lat_all(Y)
+    nzm = z["post_q_lat"] != 0
+    assert rel(ql[cu(nzm, torch.bool)], z["post_q_lat"][nzm]) < TOL
+    # seeding: fresh model + one beat (Kalman update from the GP prior), nothing else
+    seed = hb.GPI_model.fresh(z["x_basis"], z["seed_kernel"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]))
+    seed.include_weighted_sample(0, None, None, Y[4], 1.0)
+    assert seed.N == 1 and seed.A.shape[0] == 1
+    assert close(seed.f_star, z["seed_f_star"]) and close(seed.cov_f, z["seed_cov_f"])
+    assert rel(seed.compute_sq_err_all(None, Y[:, :, None]), z["seed_q"]) < TOL
+    # ... and the same through the device hyper-fit (looser: the fit itself is compared at 1e-6)
+    seed2 = hb.GPI_model.unfitted(z["x_basis"], z["noise_bounds"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]))
+    seed2.include_weighted_sample(0, None, None, Y[4], 1.0)
+    assert abs(seed2.kernel[0] - z["seed_kernel"][0]) < 1e-6 * z["seed_kernel"][0]
+    assert rel(seed2.compute_sq_err_all(None, Y[:, :, None]), z["seed_q"]) < 1e-5
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
