@@ -28,6 +28,8 @@ PROTOTYPES = {
     "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p]),
     "hgp_score_pairs": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _i64, _p, _p]),
     "hgp_snr_states": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p]),
+    "hgp_mean_beat_work_doubles": (_i64, [_int]),
+    "hgp_mean_beat": (_int, [_p, _i64, _int, _p, _p, _p]),
     "hgp_lead_weights": (_int, [_p, _p, _p, _i64, _int, _int, _p, _p, _p, _p, _p]),
     "hgp_hmm_workspace_bytes": (_i64, [_i64, _int]),
     "hgp_hmm_smooth": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p, _p, _i64,

@@ -327,3 +327,39 @@ extern "C" int hgp_rbf_kernel_matrix(const double* xa, int na, const double* xb,
     HGP_LAUNCH_CHECK("hgp_rbf_kernel_matrix");
     return 0;
 }
+
+// ---- mean beat of a lead plane: torch.mean(y_trains[:, :, ld], dim=0) in GPI_HDP.compute_snr_ini (GPI_HDP.py:715-730) ----
+// Two fixed-order stages (per-block partial sums over a contiguous slice of beats, then the blocks in order), so the
+// result does not depend on scheduling.
+namespace {
+constexpr int MEAN_BLOCKS = 256;
+__global__ void mean_beat_partial_kernel(const double* __restrict__ Y, int64_t N, int T, double* __restrict__ partial) {
+    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t n0 = blockIdx.x * per, n1 = hgp_min64(N, n0 + per);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t n = n0; n < n1; ++n) acc += Y[n * T + t];
+        partial[(int64_t)blockIdx.x * T + t] = acc;
+    }
+}
+__global__ void mean_beat_finish_kernel(const double* __restrict__ partial, int nblocks, int64_t N, int T,
+                                        double* __restrict__ mean) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * T + t];
+    mean[t] = acc / (double)N;
+}
+}  // namespace
+
+extern "C" int64_t hgp_mean_beat_work_doubles(int T) { return (int64_t)MEAN_BLOCKS * T; }
+
+extern "C" int hgp_mean_beat(const double* Y, int64_t N, int T, double* mean, double* work, void* stream) {
+    HGP_REQUIRE(N > 0 && T > 0, "hgp_mean_beat: need N > 0, T > 0");
+    const int nblocks = (int)hgp_min64(MEAN_BLOCKS, N);
+    mean_beat_partial_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(Y, N, T, work);
+    HGP_LAUNCH_CHECK("hgp_mean_beat: partial");
+    mean_beat_finish_kernel<<<(T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(work, nblocks, N, T, mean);
+    HGP_LAUNCH_CHECK("hgp_mean_beat: finish");
+    return 0;
+}

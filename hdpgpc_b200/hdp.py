@@ -349,6 +349,41 @@ class GPI_HDP:
             qbar, _, _, _ = ops.lead_weights(q_lnm, self._t(snr).permute(2, 0, 1).contiguous(), None)
         return qbar
 
+    # ---- GPI_HDP.compute_snr_ini (:715-730), normalize_snr (:750-756) ----
+    def compute_snr_ini(self, y_trains):
+        """SNR of every beat against the mean beat of its lead, softmax over leads -> self.snr_norm [N, L]."""
+        Y = self._t(y_trains)
+        N, T, L = Y.shape
+        if not self.use_snr:
+            self.snr_norm = torch.ones((N, L), dtype=F64, device=self.device)
+            return self.snr_norm
+        Yp = ops.pack_leads(Y)
+        snr = torch.empty((L, N, 1), dtype=F64, device=self.device)
+        zero = torch.zeros((N, 1), dtype=torch.int32, device=self.device)
+        for ld in range(L):
+            ops.snr_states(Yp[ld], ops.mean_beat(Yp[ld]).reshape(1, T), zero, out=snr[ld])
+        self.snr_norm = self.normalize_snr(snr.permute(1, 2, 0))
+        return self.snr_norm
+
+    def normalize_snr(self, snr):
+        """softmax over leads of the per-beat maximum over clusters; snr [N, M, L] -> [N, L]."""
+        s = self._t(snr).permute(2, 0, 1).contiguous()
+        _, _, w, _ = ops.lead_weights(torch.zeros_like(s), s, None)
+        return w
+
+    # ---- GPI_HDP.full_LDS_elbo (:1838-1864), one_sample=False ----
+    def full_LDS_elbo(self, gpmodels, sum_resp, one_sample=False):
+        """Sum over the non-empty clusters of return_LDS_param_likelihood() * N_m / N, divided by their number."""
+        from .model import lds_param_likelihood_batch
+        sr = self._t(sum_resp).reshape(-1)
+        live = [i for i in range(len(gpmodels)) if float(sr[i]) > 0]
+        if not live:
+            return torch.zeros(1, dtype=F64, device=self.device)
+        lik = lds_param_likelihood_batch([gpmodels[i] for i in live])
+        frac = sr[torch.as_tensor(live, device=self.device)] / torch.sum(sr)
+        elb = torch.sum(lik * frac).reshape(1)
+        return elb if one_sample else elb / len(live)
+
     # ---- GPI_HDP.LogLik (:632-661), axis=1 ----
     def LogLik(self, logSoftEv, axis=1):
         x = self._t(logSoftEv)

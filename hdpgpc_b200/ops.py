@@ -154,6 +154,17 @@ def snr_states(Y, mu_sm, snr_state_of, out=None):
     return snr
 
 
+def mean_beat(Y):
+    """Mean over the beats of one lead plane Y [N, T] -> [T] (fixed summation order)."""
+    lib = _lib_ready()
+    Y = _dev(Y).contiguous()
+    N, T = Y.shape
+    out = torch.empty(T, dtype=F64, device=Y.device)
+    work = torch.empty(int(lib.hgp_mean_beat_work_doubles(T)), dtype=F64, device=Y.device)
+    check(lib.hgp_mean_beat(ptr(Y), N, T, ptr(out), ptr(work), stream_ptr()), "hgp_mean_beat")
+    return out
+
+
 def lead_weights(q_lnm, snr_lnm=None, lead_w=None):
     """q, snr: [L, N, M].  Returns (qbar [N,M], e [N,M], w [N,L], any_inf flag tensor)."""
     lib = _lib_ready()

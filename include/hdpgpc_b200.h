@@ -105,6 +105,11 @@ int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const d
  * (the smoothed latent mean f_star_sm[j], j = clip(find_closest_lower(n), 1, len-1)). */
 int hgp_snr_states(const double* Y, int64_t N, int T, const double* mu_sm, const int* snr_state_of,
                    int M, double* snr, void* stream);
+/* Mean beat of one lead plane (GPI_HDP.compute_snr_ini, GPI_HDP.py:715-730: the SNR of every beat against the mean
+ * beat is hgp_snr_states with this single row as the table; softmax over leads is hgp_lead_weights' w).
+ * work: hgp_mean_beat_work_doubles(T) doubles. */
+int64_t hgp_mean_beat_work_doubles(int T);
+int hgp_mean_beat(const double* Y, int64_t N, int T, double* mean, double* work, void* stream);
 /* q, snr: [L, N, M] planes.  w[n, ld] = softmax_ld( max_m snr[ld, n, m] ) (or lead_w[N, L] when snr is
  * NULL: the saved self.snr_norm), qbar[n, m] = sum_ld q[ld, n, m] w[n, ld];
  * e[n, k] = nan_to_num(exp(qn - rowmax(qn)), 1e-8) with qn = qbar - rowmax(qbar), the subtraction

@@ -555,6 +555,13 @@ def online_steps():
     out["noise_bounds"] = np.array(sw.kernel_def.k2.noise_level_bounds)
     out["ini_sigma_def"] = np.float64(sw.ini_sigma_def)
     out["ini_gamma_def"] = np.float64(sw.ini_gamma_def)
+    # initial lead weights (GPI_HDP.compute_snr_ini :715-730) of a two-lead batch
+    data2, _ = load_record("102", 40, [0, 1], 3)
+    sw2, _, _, _ = make_model(data2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sw2.compute_snr_ini(data2)
+    out["ini2_data"] = data2
+    out["ini2_snr_norm"] = npy(sw2.snr_norm)
     path = os.path.join(HERE, "online_steps_T30.npz")
     np.savez_compressed(path, **out)
     print(f"online_steps_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")

@@ -459,6 +459,30 @@ def test_online_seam_steps_vs_reference(golden):
     assert rel(seed2.compute_sq_err_all(None, Y[:, :, None]), z["seed_q"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2"])
+def test_snr_ini_and_elbo_mirror(golden, name):
+    """GPI_HDP.compute_snr_ini (GPI_HDP.py:715-730), normalize_snr (:750-756) and full_LDS_elbo (:1838-1864) of the
+    mirror class against the reference's saved snr_norm / ELBO terms."""
+    import hdpgpc_b200 as hb
+    z = golden(name)
+    M, L = int(z["M"]), int(z["L"])
+    gps = [[hb.GPI_model.from_dump(z, f"gp_{ld}_{m}_") for m in range(M)] for ld in range(L)]
+    dev = hb.GPI_HDP(gps, z["transTheta"], z["startTheta"])
+    w = dev.compute_snr_ini(z["data"])
+    Yd = z["data"]
+    snr0 = np.stack([[O.snr_db(Yd[n, :, ld], Yd[:, :, ld].mean(axis=0)) for ld in range(L)] for n in range(Yd.shape[0])])
+    assert np.max(np.abs(w.cpu().numpy() - O.softmax(snr0, axis=1))) < 1e-10
+    wn = dev.normalize_snr(z["snr_all"])
+    e = np.exp(z["snr_all"].max(axis=1) - z["snr_all"].max(axis=1).max(axis=1, keepdims=True))
+    assert np.max(np.abs(wn.cpu().numpy() - e / e.sum(axis=1, keepdims=True))) < 1e-12
+    for ld in range(L):
+        elb = float(dev.full_LDS_elbo(gps[ld], z["train_Nm"]))
+        assert abs(elb - z["elbo_full_LDS"][ld]) < TOL * abs(z["elbo_full_LDS"][ld])
+    z2 = golden("online_steps_T30")       # compute_snr_ini as the reference computed it on a two-lead batch
+    w2 = dev.compute_snr_ini(z2["ini2_data"])
+    assert np.max(np.abs(w2.cpu().numpy() - z2["ini2_snr_norm"])) < 1e-10
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
