@@ -311,6 +311,28 @@ __global__ void stats_finish_kernel(const int* __restrict__ counts, const double
     (void)pair0_is_dummy;
 }
 
+// The forward and the backward scan are independent: the backward one runs on a side stream (fork / join with events)
+// so that the two latency-bound chunk scans share the SMs instead of following each other.
+struct HmmSide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+};
+static HmmSide* hmm_side() {
+    static thread_local HmmSide side;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (side.device != dev) {
+        if (side.stream) { cudaStreamDestroy(side.stream); cudaEventDestroy(side.fork); cudaEventDestroy(side.join); }
+        side = HmmSide();
+        if (cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        side.device = dev;
+    }
+    return &side;
+}
+
 template <int KP>
 int launch_scans(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
                  const double* boundary_in, int has_prev, int has_next, double* alpha, double* beta, double* marg,
@@ -320,14 +342,21 @@ int launch_scans(const double* e, int64_t N, int K, const double* pi, const doub
     const int threads = 4 * KP;
     double* fa[2] = {endsA, endsA + C * K};
     double* fb[2] = {endsB, endsB + C * K};
+    HmmSide* side = hmm_side();
+    if (!side) { hgp_set_error("hgp_hmm_smooth: cannot create the side stream"); return HGP_E_UNSUPPORTED; }
+    cudaStream_t sb = side->stream;      // backward direction
     cudaMemsetAsync(changed, 0, 2 * sizeof(int), st);
     if (!warm) {
+    cudaEventRecord(side->fork, st);
+    cudaStreamWaitEvent(sb, side->fork, 0);
     hmm_scan_kernel<KP, false><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, PiT, boundary_in, has_prev, alpha,
                                                                  marg, nullptr, fa[0], changed, 0, 0);
     HGP_LAUNCH_CHECK("hmm forward scan");
-    hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr,
+    hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, sb>>>(e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr,
                                                                 has_next, beta, nullptr, nullptr, fb[0], changed + 1, 0, 0);
     HGP_LAUNCH_CHECK("hmm backward scan");
+    cudaEventRecord(side->join, sb);
+    cudaStreamWaitEvent(st, side->join, 0);
     }
     int rounds = 0;
     if (C > 1 || warm) {
@@ -336,16 +365,22 @@ int launch_scans(const double* e, int64_t N, int K, const double* pi, const doub
         int first_rebase = warm;     // warm start: the first repair round also re-scans the two boundary chunks
         while (need_f || need_b) {
             cudaMemsetAsync(changed, 0, 2 * sizeof(int), st);
+            if (need_b) {
+                cudaEventRecord(side->fork, st);
+                cudaStreamWaitEvent(sb, side->fork, 0);
+            }
             if (need_f) {
                 hmm_scan_kernel<KP, false><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, PiT, boundary_in, has_prev,
                                                                              alpha, marg, fa[cur], fa[cur ^ 1], changed, 1, first_rebase);
                 HGP_LAUNCH_CHECK("hmm forward repair");
             }
             if (need_b) {
-                hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, st>>>(
+                hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, sb>>>(
                     e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr, has_next, beta, nullptr, fb[cur], fb[cur ^ 1],
                     changed + 1, 1, first_rebase);
                 HGP_LAUNCH_CHECK("hmm backward repair");
+                cudaEventRecord(side->join, sb);
+                cudaStreamWaitEvent(st, side->join, 0);
             }
             cudaError_t er = cudaMemcpyAsync(changed_host, changed, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
             if (er != cudaSuccess) return hgp_status(er, "hmm repair flag copy");

@@ -21,7 +21,6 @@
 //     triangular shrinkage stays balanced over the 4 SM sub-partitions; each warp keeps its 32 x 64 slice of z in
 //     registers (64 f64 accumulators per lane).
 #include "hgp_common.cuh"
-#include <type_traits>
 
 namespace {
 
