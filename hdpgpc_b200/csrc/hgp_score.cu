@@ -119,18 +119,31 @@ __device__ __forceinline__ void fast_step(double (&acc)[4][8][2], uint32_t it, i
     const int stage = it % STAGES;
     const double2* ya = reinterpret_cast<const double2*>(Yfrag + s * Y_CHUNK_DOUBLES) + lane;
     double2 b[8];
+#ifdef HGP_NO_FRAGLOAD
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) b[nt] = make_double2(1.0 + nt, 2.0 + lane);
+    (void)ya;
+#else
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) b[nt] = ya[nt * 32];      // the beat fragments do not depend on the pipeline
+#endif
+#ifndef HGP_NO_BAR
     mbar_wait(&full_bar[stage], (it / STAGES) & 1);
+#endif
     const double2* ws = reinterpret_cast<const double2*>(Wst + stage * W_STAGE_BYTES) + lane;
     {
         // chunk s: block rb sits at (rb - s) * 512 bytes
         const double2* wa = ws - s * 32;
         double2 a[4];
+#ifdef HGP_NO_FRAGLOAD
+        a[0] = a[1] = a[2] = a[3] = make_double2(0.5 * lane, 0.25 * s);
+        (void)wa;
+#else
         if (JA <= 0) a[0] = wa[rb0 * 32];
         if (JA <= 1) a[1] = wa[rb1 * 32];
         if (JA <= 2) a[2] = wa[rb2 * 32];
         if (JA <= 3) a[3] = wa[rb3 * 32];
+#endif
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (j >= JA) {
@@ -144,11 +157,16 @@ __device__ __forceinline__ void fast_step(double (&acc)[4][8][2], uint32_t it, i
     if (JB < 4) {
         // chunk 31 - s follows the 32 - s blocks of chunk s: block rb sits at (32 - s + rb - (31 - s)) = (rb + 1) * 512
         const double2* yb = reinterpret_cast<const double2*>(Yfrag + (MAX_NRB - 1 - s) * Y_CHUNK_DOUBLES) + lane;
+        double2 a[4];
+#ifdef HGP_NO_FRAGLOAD
+        a[2] = a[3] = make_double2(0.125 * lane, 0.75 * s);
+        (void)yb;
+#else
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) b[nt] = yb[nt * 32];
-        double2 a[4];
         if (JB <= 2) a[2] = ws[(rb2 + 1) * 32];
         if (JB <= 3) a[3] = ws[(rb3 + 1) * 32];
+#endif
 #pragma unroll
         for (int j = 2; j < 4; ++j) {
             if (j >= JB) {
@@ -159,8 +177,10 @@ __device__ __forceinline__ void fast_step(double (&acc)[4][8][2], uint32_t it, i
             }
         }
     }
+#ifndef HGP_NO_BAR
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[stage]);
+#endif
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 1)
@@ -210,7 +230,11 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
             const int m_end = min(M, m_begin + m_per_item);
             load_beat_tile(Yfrag, Y, N, T, nrb, tile * BT, warp, lane);
             __syncthreads();   // tile complete (all warps load it)
+#ifdef HGP_NO_BAR
+            if (false) {
+#else
             if (warp == NCW && lane == 0) {
+#endif
                 for (int m = m_begin; m < m_end; ++m) {
                     const unsigned char* Wp =
                         reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
