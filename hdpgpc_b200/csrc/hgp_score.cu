@@ -183,11 +183,33 @@ __device__ __forceinline__ void fast_step(double (&acc)[4][8][2], uint32_t it, i
 #endif
 }
 
+// Work items of the persistent loop: item < n_coarse is (tile, run of m_per_item clusters).  The items that would form
+// the last, partially filled round of the grid are cut into `fine` pieces each, so that the tail costs a fraction of a
+// coarse item instead of a whole one (6252 coarse items over 148 SMs: 43 rounds for 42.24 rounds of work).
+struct TileItem { int64_t tile; int m_begin, m_end; };
+__device__ __forceinline__ TileItem decode_item(int64_t item, int64_t n_coarse, int m_splits, int m_per_item, int fine, int M) {
+    int64_t coarse = item;
+    int part = 0, parts = 1;
+    if (item >= n_coarse) {
+        coarse = n_coarse + (item - n_coarse) / fine;
+        part = (int)((item - n_coarse) % fine);
+        parts = fine;
+    }
+    TileItem r;
+    r.tile = coarse / m_splits;
+    const int mb = (int)(coarse % m_splits) * m_per_item;
+    const int me = min(M, mb + m_per_item);
+    const int len = (me - mb + parts - 1) / parts;
+    r.m_begin = min(me, mb + part * len);
+    r.m_end = min(me, r.m_begin + len);
+    return r;
+}
+
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ nu,
                    const double* __restrict__ Wpacked, int64_t packed_doubles, const int* __restrict__ state_of,
                    const int* __restrict__ tile_state, const int* __restrict__ factor_of_cluster, int M, int m_per_item,
-                   int m_splits, int64_t n_items, double* __restrict__ q) {
+                   int m_splits, int64_t n_items, int64_t n_coarse, int fine, double* __restrict__ q) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nrb = (T + 7) / 8;
     const TileSmem lay = tile_smem_layout(nrb);
@@ -225,9 +247,9 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
         // ===================================== producer =====================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HGP_PRODUCER_REGS));
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int64_t tile = item / m_splits;
-            const int m_begin = (int)(item % m_splits) * m_per_item;
-            const int m_end = min(M, m_begin + m_per_item);
+            const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+            const int64_t tile = wi.tile;
+            const int m_begin = wi.m_begin, m_end = wi.m_end;
             load_beat_tile(Yfrag, Y, N, T, nrb, tile * BT, warp, lane);
             __syncthreads();   // tile complete (all warps load it)
 #ifdef HGP_NO_BAR
@@ -285,9 +307,9 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
         const int rb_of[4] = {warp, 15 - warp, 16 + warp, 31 - warp};
         const int qrow = lane >> 2;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int64_t tile = item / m_splits;
-            const int m_begin = (int)(item % m_splits) * m_per_item;
-            const int m_end = min(M, m_begin + m_per_item);
+            const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+            const int64_t tile = wi.tile;
+            const int m_begin = wi.m_begin, m_end = wi.m_end;
             const int64_t n0 = tile * BT;
             load_beat_tile(Yfrag, Y, N, T, nrb, n0, warp, lane);
             __syncthreads();   // tile complete
@@ -719,11 +741,20 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
     while (n_tiles * m_splits < 24 * (int64_t)n_sm && m_splits * 2 <= M && M / (m_splits * 2) >= 4) m_splits *= 2;
     const int m_per_item = (M + m_splits - 1) / m_splits;
     m_splits = (M + m_per_item - 1) / m_per_item;
-    const int64_t n_items = n_tiles * m_splits;
-    const int grid = (int)hgp_min64(n_items, n_sm);
+    const int64_t n_all = n_tiles * m_splits;
+    const int grid = (int)hgp_min64(n_all, n_sm);
+    // the coarse items of the last, partially filled round are cut into `fine` pieces (see decode_item)
+    int fine = 1;
+    int64_t n_coarse = n_all;
+    const int64_t rem = n_all % grid;
+    if (n_all > grid && rem != 0 && m_per_item >= 8) {
+        fine = 4;
+        n_coarse = n_all - rem;
+    }
+    const int64_t n_items = n_coarse + (n_all - n_coarse) * fine;
     score_tiles_kernel<<<grid, TILE_THREADS, lay.total, (cudaStream_t)stream>>>(
         Y, N, T, nu, Wpacked, hgp_packed_factor_bytes(T) / 8, state_of, tile_state, factor_of_cluster, M, m_per_item,
-        m_splits, n_items, q);
+        m_splits, n_items, n_coarse, fine, q);
     HGP_LAUNCH_CHECK("hgp_score_tiles");
     if (snr) return hgp_snr_states(Y, N, T, mu_sm, snr_state_of, M, snr, stream);
     return 0;
