@@ -58,6 +58,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// every warp but the one that streams the factors: beat-tile hand-over at the item boundaries
+__device__ __forceinline__ void tile_bar() { asm volatile("bar.sync 2, 352;" ::: "memory"); }
 
 #ifdef HGP_NO_MMA   // experiment: everything but the tensor-core instruction (operands stay live)
 __device__ __forceinline__ void tile_mma(double& c0, double& c1, double a, double b) { asm volatile("" ::"d"(a), "d"(b), "d"(c0), "d"(c1)); }
@@ -95,12 +97,13 @@ __host__ __device__ inline TileSmem tile_smem_layout(int nrb) {
     return s;
 }
 
-// Beat tile -> shared memory in B-fragment order, zero padded (rows n >= N, samples t >= T), by all warps of the CTA.
+// Beat tile -> shared memory in B-fragment order, zero padded (rows n >= N, samples t >= T), by 11 of the 12 warps.
 // Sample t of beat c goes to chunk t/8, double2 slot (c/8)*32 + (c%8)*4 + t%4, component (t%8)/4: the lane that owns
 // column c%8 and k-index t%4 of n-tile c/8 finds both of its k-steps in one 16-byte load.
 __device__ __forceinline__ void load_beat_tile(double* Yfrag, const double* __restrict__ Y, int64_t N, int T, int nrb,
                                                int64_t n0, int warp, int lane) {
-    for (int c = warp; c < BT; c += NCW + NPW) {
+    // loaders: every warp but the factor streamer (warp NCW)
+    for (int c = warp < NCW ? warp : warp - 1; c < BT; c += NCW + NPW - 1) {
         const int64_t n = n0 + c;
         const double* src = Y + n * T;
         double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
@@ -246,35 +249,39 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
     if (warp >= NCW) {
         // ===================================== producer =====================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HGP_PRODUCER_REGS));
+        if (warp == NCW) {
+            // The factor stream does not depend on the beat tile: this warp stays out of the item barriers and keeps
+            // the ring full across item boundaries, bounded only by the consumers' empty-barrier arrivals.
+            if (lane == 0) {
+                for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                    const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+                    for (int m = wi.m_begin; m < wi.m_end; ++m) {
+                        const unsigned char* Wp =
+                            reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
+                        for (int st = 0; st < n_steps; ++st, ++it) {
+                            const int ka = st, kb = nrb - 1 - st;
+                            const bool two = kb > ka;
+                            const int stage = it % STAGES;
+                            const uint32_t bytes_a = (uint32_t)(nrb - ka) * 512u;
+                            const uint32_t bytes_b = two ? (uint32_t)(nrb - kb) * 512u : 0u;
+                            const uint32_t off_a = 512u * (uint32_t)(ka * nrb - (ka * (ka - 1)) / 2);
+                            const uint32_t off_b = 512u * (uint32_t)(kb * nrb - (kb * (kb - 1)) / 2);
+                            mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&full_bar[stage], bytes_a + bytes_b);
+                            bulk_g2s(Wst + stage * W_STAGE_BYTES, Wp + off_a, bytes_a, &full_bar[stage]);
+                            if (two) bulk_g2s(Wst + stage * W_STAGE_BYTES + bytes_a, Wp + off_b, bytes_b, &full_bar[stage]);
+                        }
+                    }
+                }
+            }
+            return;
+        }
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
             const int64_t tile = wi.tile;
             const int m_begin = wi.m_begin, m_end = wi.m_end;
             load_beat_tile(Yfrag, Y, N, T, nrb, tile * BT, warp, lane);
-            __syncthreads();   // tile complete (all warps load it)
-#ifdef HGP_NO_BAR
-            if (false) {
-#else
-            if (warp == NCW && lane == 0) {
-#endif
-                for (int m = m_begin; m < m_end; ++m) {
-                    const unsigned char* Wp =
-                        reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
-                    for (int st = 0; st < n_steps; ++st, ++it) {
-                        const int ka = st, kb = nrb - 1 - st;
-                        const bool two = kb > ka;
-                        const int stage = it % STAGES;
-                        const uint32_t bytes_a = (uint32_t)(nrb - ka) * 512u;
-                        const uint32_t bytes_b = two ? (uint32_t)(nrb - kb) * 512u : 0u;
-                        const uint32_t off_a = 512u * (uint32_t)(ka * nrb - (ka * (ka - 1)) / 2);
-                        const uint32_t off_b = 512u * (uint32_t)(kb * nrb - (kb * (kb - 1)) / 2);
-                        mbar_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], bytes_a + bytes_b);
-                        bulk_g2s(Wst + stage * W_STAGE_BYTES, Wp + off_a, bytes_a, &full_bar[stage]);
-                        if (two) bulk_g2s(Wst + stage * W_STAGE_BYTES + bytes_a, Wp + off_b, bytes_b, &full_bar[stage]);
-                    }
-                }
-            }
+            tile_bar();   // tile complete (every warp but the factor streamer loads it)
             if (warp == NCW + 1) {
                 // Reducer: the consumers never meet at a CTA barrier for the per-beat sum over the eight warps' partial
                 // |z|^2 -- they drop their partials into a double-buffered array, arrive on an mbarrier and move on to
@@ -298,7 +305,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                     if (lane == 0) mbar_arrive(&epi_free[b]);
                 }
             }
-            __syncthreads();   // consumers are done with this item; the beat tile may be rewritten
+            tile_bar();   // consumers are done with this item; the beat tile may be rewritten
         }
     } else {
         // ===================================== consumers =====================================
@@ -312,7 +319,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
             const int m_begin = wi.m_begin, m_end = wi.m_end;
             const int64_t n0 = tile * BT;
             load_beat_tile(Yfrag, Y, N, T, nrb, n0, warp, lane);
-            __syncthreads();   // tile complete
+            tile_bar();   // tile complete
             for (int m = m_begin; m < m_end; ++m) {
                 double acc[4][8][2];
 #pragma unroll
@@ -448,7 +455,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                 if (lane == 0) mbar_arrive(&epi_full[epi & 1]);
                 ++epi;
             }
-            __syncthreads();   // matches the producer's end-of-item barrier
+            tile_bar();   // matches the donor warps' end-of-item barrier
         }
     }
 }
