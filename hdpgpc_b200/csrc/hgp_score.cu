@@ -503,36 +503,56 @@ score_pairs_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                    const double* __restrict__ W, const int* __restrict__ state_of,
                    const int* __restrict__ factor_of_state, int M, const int* __restrict__ pair_n,
                    const int* __restrict__ pair_m, int64_t n_pairs, double* __restrict__ q) {
+    // One CTA per pair (persistent over pairs): the residual d = y - mu sits in shared memory, the eight warps take the
+    // rows r = w, w + 8, ... of the triangular product, two rows per trip so that two row loads are in flight, and the
+    // eight partial sums are added in a fixed order.  (One warp per pair left a short exception list -- the 64 `first`
+    // pairs of a cfg4 lead plane -- latency-bound at 0.35 ms; a CTA per pair is 8x shorter and moves the same bytes
+    // when every state has its own factor.)
     extern __shared__ double dsm[];
+    __shared__ double s_part[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* d = dsm + warp * T;
-    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; p < n_pairs; p += wstride) {
+    double* d = dsm;
+    for (int64_t p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         int64_t n;
         int m;
         if (pair_n) { n = pair_n[p]; m = pair_m[p]; }
         else { n = p / M; m = (int)(p % M); }
         const int s = state_of[n * M + m];
         if (s < 0) {
-            if (lane == 0) q[n * M + m] = 0.0;
+            if (threadIdx.x == 0) q[n * M + m] = 0.0;
             continue;
         }
         const int64_t f = factor_of_state ? factor_of_state[s] : s;
         const double* Wf = W + f * (int64_t)T * T;
         const double* yrow = Y + n * T;
         const double* mrow = mu + (int64_t)s * T;
-        __syncwarp();
-        for (int t = lane; t < T; t += 32) d[t] = yrow[t] - mrow[t];
-        __syncwarp();
+        __syncthreads();            // previous pair's readers of d / s_part are done
+        for (int t = threadIdx.x; t < T; t += blockDim.x) d[t] = yrow[t] - mrow[t];
+        __syncthreads();
         double acc = 0.0;
-        for (int r = 0; r < T; ++r) {
-            const double* wr = Wf + (int64_t)r * T;
-            double part = 0.0;
-            for (int k = lane; k <= r; k += 32) part += wr[k] * d[k];
-            part = warp_sum(part);
-            acc += part * part;
+        for (int r = warp; r < T; r += 16) {
+            const int r2 = r + 8;
+            const double* w0 = Wf + (int64_t)r * T;
+            const double* w1 = Wf + (int64_t)r2 * T;
+            double p0 = 0.0, p1 = 0.0;
+            for (int k = lane; k <= r; k += 32) p0 += w0[k] * d[k];
+            if (r2 < T)
+                for (int k = lane; k <= r2; k += 32) p1 += w1[k] * d[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            }
+            acc += p0 * p0 + p1 * p1;
         }
-        if (lane == 0) q[n * M + m] = -0.5 * acc - 0.5 * (double)T * HGP_LOG2PI;
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_part[w];
+            q[n * M + m] = -0.5 * tot - 0.5 * (double)T * HGP_LOG2PI;
+        }
     }
 }
 
@@ -774,14 +794,9 @@ extern "C" int hgp_score_pairs(const double* Y, int64_t N, int T, const double* 
     HGP_REQUIRE(T <= 1024, "hgp_score_pairs: need T <= 1024");
     HGP_REQUIRE((pair_n == nullptr) == (pair_m == nullptr), "hgp_score_pairs: pair_n/pair_m must both be given");
     if (n_pairs == 0) return 0;
-    const int warps = 8;
-    size_t smem = sizeof(double) * warps * T;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(score_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return hgp_status(e, "hgp_score_pairs: smem attribute");
-    }
-    int blocks = (int)hgp_min64((n_pairs + warps - 1) / warps, 148 * 8);
-    score_pairs_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(Y, N, T, mu, W, state_of, factor_of_state,
+    const size_t smem = sizeof(double) * T;
+    const int blocks = (int)hgp_min64(n_pairs, 148 * 8);
+    score_pairs_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(Y, N, T, mu, W, state_of, factor_of_state,
                                                                           M, pair_n, pair_m, n_pairs, q);
     HGP_LAUNCH_CHECK("hgp_score_pairs");
     return 0;
