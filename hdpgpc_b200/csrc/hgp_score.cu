@@ -21,6 +21,7 @@
 //     triangular shrinkage stays balanced over the 4 SM sub-partitions; each warp keeps its 32 x 64 slice of z in
 //     registers (64 f64 accumulators per lane).
 #include "hgp_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -689,6 +690,179 @@ snr_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* _
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// SNR statistic on the tensor cores.  sum (mu - y)^2 = sum mu^2 - 2 mu.y + sum y^2: the cross term of the (at most
+// M + 64) distinct state rows a 64-beat tile can meet against the tile's beats is a dense product V Y^T -- the same B
+// operand as the score kernel (beat tile in B-fragment order), a gathered, non-triangular A operand.  The scalar
+// kernel above spends 77 warp instructions per (beat, cluster) pair, most of them in 32-lane reductions; here a pair
+// costs 1/8 of a DMMA plus one log10.
+//   * rows: thread m scans cluster m down the tile and emits one row per distinct state (the index only advances
+//     at the cluster's own members, so there are at most M + 64 rows);
+//   * A operand: streamed in groups of 32 columns; warp w always supplies row w of every 8-row block (a coalesced
+//     256-byte read per row), scatters it into A-fragment order in shared memory and accumulates sum mu^2 of its rows
+//     on the way (fixed order); the next group is prefetched into registers under the current group's DMMAs;
+//   * warp w multiplies row blocks w, w + 8 (, w + 16) against all eight n-tiles;
+//   * epilogue: element (row, beat) is the pair (beat, cluster of the row) iff the beat's state for that cluster is
+//     the row's state; noise = sum mu^2 - 2 cross + sum y^2, recomputed directly in the rare case where the expansion
+//     would cancel more than five digits (SNR > 50 dB).
+constexpr int SNRM_BT = 64;
+template <int RBW>   // row blocks per warp: 2 (M <= 64) or 3 (M <= 128)
+__global__ void __launch_bounds__(256, 1)
+snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
+               const int* __restrict__ snr_state_of, int M, double* __restrict__ snr) {
+    constexpr int NRB = 8 * RBW;            // row blocks per tile
+    constexpr int NROW = 8 * NRB;           // rows (padded)
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int nrb = (T + 7) / 8;            // k-chunks
+    double* Yfrag = reinterpret_cast<double*>(smraw);                    // [nrb][512]
+    double* Ast = Yfrag + nrb * Y_CHUNK_DOUBLES;                         // [4][NRB][64]
+    double* ysq = Ast + 4 * NRB * 64;                                    // [64]
+    double* row_sig = ysq + SNRM_BT;                                     // [NROW]
+    int* row_s = reinterpret_cast<int*>(row_sig + NROW);                 // [NROW]
+    int* row_m = row_s + NROW;                                           // [NROW]
+    int* cnt = row_m + NROW;                                             // [M + 1]
+    int* sstate = cnt + ((M + 2) & ~1);                                  // [64][M]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (N + SNRM_BT - 1) / SNRM_BT;
+    const int n_groups = (nrb + 3) / 4;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t n0 = tile * SNRM_BT;
+        const int nb = (int)hgp_min64(SNRM_BT, N - n0);
+        __syncthreads();                     // previous tile's readers are done
+        // ---- beat tile in B-fragment order + sum y^2 per beat; state indices of the tile
+        for (int c = warp; c < SNRM_BT; c += 8) {
+            const int64_t n = n0 + c;
+            double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
+            double p = 0.0;
+            for (int t = lane; t < nrb * 8; t += 32) {
+                const double v = (c < nb && t < T) ? __ldg(Y + n * T + t) : 0.0;
+                base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = v;
+                p += v * v;
+            }
+            p = warp_sum(p);
+            if (lane == 0) ysq[c] = p;
+        }
+        for (int i = tid; i < SNRM_BT * M; i += 256) {
+            const int b = i / M;
+            sstate[i] = (b < nb) ? snr_state_of[n0 * M + i] : -3;        // -3: beat outside the sequence, matches no row
+        }
+        __syncthreads();
+        // ---- rows: one per distinct state of every cluster
+        if (tid < M) {
+            int c = 0, prev = -2;
+            for (int b = 0; b < nb; ++b) {
+                const int sb = sstate[b * M + tid];
+                if (sb != prev) { ++c; prev = sb; }
+            }
+            cnt[tid] = c;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int m = 0; m < M; ++m) { const int c = cnt[m]; cnt[m] = acc; acc += c; }
+            cnt[M] = acc;
+        }
+        __syncthreads();
+        const int n_rows = cnt[M];
+        if (tid < M) {
+            int r = cnt[tid], prev = -2;
+            for (int b = 0; b < nb; ++b) {
+                const int sb = sstate[b * M + tid];
+                if (sb != prev) { row_s[r] = sb; row_m[r] = tid; ++r; prev = sb; }
+            }
+        }
+        for (int r = n_rows + tid; r < NROW; r += 256) { row_s[r] = -1; row_m[r] = -1; }
+        __syncthreads();
+
+        // ---- product: acc[j][nt] for row blocks rb = warp + 8 j
+        double acc[RBW][8][2];
+#pragma unroll
+        for (int j = 0; j < RBW; ++j)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) acc[j][nt][0] = acc[j][nt][1] = 0.0;
+        double pre[NRB], rsq[NRB];
+#pragma unroll
+        for (int i = 0; i < NRB; ++i) rsq[i] = 0.0;
+        auto fetch = [&](int g) {
+            const int col = g * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < NRB; ++i) {
+                const int sr = row_s[warp + 8 * i];
+                pre[i] = (sr >= 0 && col < T) ? __ldg(mu_sm + (int64_t)sr * T + col) : 0.0;
+            }
+        };
+        fetch(0);
+        for (int g = 0; g < n_groups; ++g) {
+            // scatter the prefetched group into A-fragment order: row-in-block = warp, column lane
+            {
+                const int j = lane >> 3, cc = lane & 7;
+                double* dst = Ast + ((j * NRB) * 32 + warp * 4 + (cc & 3)) * 2 + (cc >> 2);
+#pragma unroll
+                for (int i = 0; i < NRB; ++i) {
+                    dst[i * 64] = pre[i];
+                    rsq[i] += pre[i] * pre[i];
+                }
+            }
+            __syncthreads();
+            if (g + 1 < n_groups) fetch(g + 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = g * 4 + j;
+                if (kc < nrb) {
+                    const double2* ys = reinterpret_cast<const double2*>(Yfrag + kc * Y_CHUNK_DOUBLES) + lane;
+                    double2 b[8];
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) b[nt] = ys[nt * 32];
+#pragma unroll
+                    for (int q2 = 0; q2 < RBW; ++q2) {
+                        const double2 a = reinterpret_cast<const double2*>(Ast)[(j * NRB + warp + 8 * q2) * 32 + lane];
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) dmma884(acc[q2][nt][0], acc[q2][nt][1], a.x, b[nt].x);
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) dmma884(acc[q2][nt][0], acc[q2][nt][1], a.y, b[nt].y);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < NRB; ++i) {
+            const double tot = warp_sum(rsq[i]);
+            if (lane == 0) row_sig[warp + 8 * i] = tot;
+        }
+        __syncthreads();
+        // ---- epilogue
+#pragma unroll
+        for (int j = 0; j < RBW; ++j) {
+            const int r = (warp + 8 * j) * 8 + (lane >> 2);
+            const int m = row_m[r], sr = row_s[r];
+            const double sig = row_sig[r];
+            if (m < 0) continue;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = nt * 8 + 2 * (lane & 3) + e;
+                    if (sstate[c * M + m] != sr) continue;               // also rejects beats outside the sequence
+                    double out = 0.0;
+                    if (sr >= 0) {
+                        double noi = sig - 2.0 * acc[j][nt][e] + ysq[c];
+                        if (noi < 1e-5 * (sig + ysq[c])) {
+                            // the expansion would lose more than five digits: direct sum for this pair
+                            const double* mr = mu_sm + (int64_t)sr * T;
+                            const double* yr = Y + (n0 + c) * T;
+                            noi = 0.0;
+                            for (int t = 0; t < T; ++t) { const double d = mr[t] - yr[t]; noi += d * d; }
+                        }
+                        out = 10.0 * log10((sig + HGP_EPS) / (noi + HGP_EPS));
+                    }
+                    snr[(n0 + c) * M + m] = out;
+                }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 snr_states_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
                   const int* __restrict__ snr_state_of, int M, double* __restrict__ snr) {
@@ -813,7 +987,18 @@ extern "C" int hgp_snr_states(const double* Y, int64_t N, int T, const double* m
         if (e != cudaSuccess) return hgp_status(e, "hgp_snr_states: smem attribute");
     }
     int blocks = (int)hgp_min64((N + warps - 1) / warps, 148 * 8);
-    if (T <= 256) {
+    if (T <= 256 && M <= 128 && M >= 1 && !getenv("HGP_SNR_SCALAR")) {   // never a function of N: a sliced sweep must take the same path
+        const int nrbk = (T + 7) / 8;
+        const int rbw = M <= 64 ? 2 : 3;
+        const int nrow = 64 * rbw;
+        const size_t msm = sizeof(double) * ((size_t)nrbk * Y_CHUNK_DOUBLES + 4 * 8 * rbw * 64 + SNRM_BT + nrow) +
+                           sizeof(int) * (2 * (size_t)nrow + ((M + 2) & ~1) + (size_t)SNRM_BT * M) + 16;
+        auto kern = rbw == 2 ? snr_mma_kernel<2> : snr_mma_kernel<3>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_snr_states: smem attribute");
+        const int mblocks = (int)hgp_min64((N + SNRM_BT - 1) / SNRM_BT, 148);
+        kern<<<mblocks, 256, msm, (cudaStream_t)stream>>>(Y, N, T, mu_sm, snr_state_of, M, snr);
+    } else if (T <= 256) {
         const size_t tsm = sizeof(double) * SNR_BT * T;          // <= 64 KB: three CTAs per SM
         const int tblocks = (int)hgp_min64((N + SNR_BT - 1) / SNR_BT, 148 * 3);
         auto kern = T <= 128 ? snr_tiles_kernel<4> : snr_tiles_kernel<8>;

@@ -734,6 +734,37 @@ def test_sharded_hmm_emulated_ranks_bitwise():
     assert torch.equal(warm.zpair, cold.zpair) and torch.equal(warm.boundary_out, cold.boundary_out)
 
 
+@pytest.mark.parametrize("N,T,M", [(1000, 256, 64), (777, 90, 5), (300, 64, 100), (4096, 256, 128), (260, 17, 3)])
+def test_snr_tensor_core_path_vs_scalar_and_oracle(N, T, M):
+    """hgp_snr_states on the tensor cores (cross term mu.y as a dense product per 64-beat tile, N >= 256) against the
+    scalar kernel and the oracle: ragged last tile, T not a multiple of 8, M up to 128, empty clusters, and a beat that
+    equals its state mean (infinite SNR: the direct fallback must reproduce the reference's eps-regularised value)."""
+    import os
+    from hdpgpc_b200 import ops, synthetic
+    wl = synthetic.make_workload(N, T=T, L=1, M=M, seed=N + T + M, device="cuda")
+    tb = wl["leads"][0]
+    Y = ops.pack_leads(wl["Y"])[0].clone()
+    mu_sm, sso = tb["mu_sm"], tb["snr_state_of"].clone()
+    sso[:, M - 1] = -1                                            # an empty cluster
+    n_eq = N // 2
+    s_eq = int(sso[n_eq, 0])
+    if s_eq >= 0:
+        Y[n_eq] = mu_sm[s_eq]                                     # noise exactly zero for (n_eq, cluster 0)
+    fast = ops.snr_states(Y, mu_sm, sso)
+    os.environ["HGP_SNR_SCALAR"] = "1"
+    try:
+        slow = ops.snr_states(Y, mu_sm, sso)
+    finally:
+        del os.environ["HGP_SNR_SCALAR"]
+    want = cu(O.snr_states(Y.cpu().numpy(), mu_sm.cpu().numpy(), sso.clamp_min(0).cpu().numpy()))
+    want[sso < 0] = 0.0                                           # empty cluster: the statistic is defined as 0
+    assert torch.all(fast[:, M - 1] == 0) and torch.all(slow[:, M - 1] == 0)
+    err = lambda a: float(torch.max(torch.abs(a - want) / torch.clamp(torch.abs(want), min=1.0)))
+    assert err(slow) < TOL and err(fast) < TOL
+    if s_eq >= 0 and float(torch.sum(mu_sm[s_eq] ** 2)) > 0:
+        assert float(fast[n_eq, 0]) > 100.0 and abs(float(fast[n_eq, 0]) - float(want[n_eq, 0])) < 1e-6
+
+
 def test_sweep_from_host_equals_resident_sweep():
     """The end-to-end call (pinned host beats, sliced H2D copies overlapped with scoring) gives bitwise the same scores,
     labels and statistics as the device-resident sweep, for a beat count that is not a multiple of the slice size."""
