@@ -108,8 +108,19 @@ __device__ __forceinline__ void load_beat_tile(double* Yfrag, const double* __re
         const int64_t n = n0 + c;
         const double* src = Y + n * T;
         double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
-        for (int t = lane; t < nrb * 8; t += 32)
-            base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = (n < N && t < T) ? __ldg(src + t) : 0.0;
+        // all (up to eight) loads of the row first: with a run-time trip count the loop would wait out one memory
+        // latency per 32 samples
+        double v[MAX_NRB / 4];
+#pragma unroll
+        for (int k = 0; k < MAX_NRB / 4; ++k) {
+            const int t = lane + 32 * k;
+            v[k] = (n < N && t < T) ? __ldg(src + t) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < MAX_NRB / 4; ++k) {
+            const int t = lane + 32 * k;
+            if (t < nrb * 8) base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = v[k];
+        }
     }
 }
 
@@ -704,7 +715,7 @@ snr_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* _
 //   * warp w multiplies row blocks w, w + 8 (, w + 16) against all eight n-tiles;
 //   * epilogue: element (row, beat) is the pair (beat, cluster of the row) iff the beat's state for that cluster is
 //     the row's state; noise = sum mu^2 - 2 cross + sum y^2, recomputed directly in the rare case where the expansion
-//     would cancel more than five digits (SNR > 50 dB).
+//     would cancel more than eight digits (SNR > 80 dB).
 constexpr int SNRM_BT = 64;
 template <int RBW>   // row blocks per warp: 2 (M <= 64) or 3 (M <= 128)
 __global__ void __launch_bounds__(256, 1)
@@ -734,11 +745,17 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
         for (int c = warp; c < SNRM_BT; c += 8) {
             const int64_t n = n0 + c;
             double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
-            double p = 0.0;
-            for (int t = lane; t < nrb * 8; t += 32) {
-                const double v = (c < nb && t < T) ? __ldg(Y + n * T + t) : 0.0;
-                base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = v;
-                p += v * v;
+            double p = 0.0, v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {        // all loads of the row in flight at once (T <= 256)
+                const int t = lane + 32 * k;
+                v[k] = (c < nb && t < T) ? __ldg(Y + n * T + t) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = lane + 32 * k;
+                if (t < nrb * 8) base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = v[k];
+                p += v[k] * v[k];
             }
             p = warp_sum(p);
             if (lane == 0) ysq[c] = p;
@@ -848,8 +865,9 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
                     double out = 0.0;
                     if (sr >= 0) {
                         double noi = sig - 2.0 * acc[j][nt][e] + ysq[c];
-                        if (noi < 1e-5 * (sig + ysq[c])) {
-                            // the expansion would lose more than five digits: direct sum for this pair
+                        if (noi < 1e-8 * (sig + ysq[c])) {
+                            // the expansion would lose more than eight digits (the dB value would be off by more than
+                            // 4e-8 absolute at 80 dB): direct sum for this pair
                             const double* mr = mu_sm + (int64_t)sr * T;
                             const double* yr = Y + (n0 + c) * T;
                             noi = 0.0;
