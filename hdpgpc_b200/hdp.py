@@ -313,6 +313,7 @@ class GPI_HDP:
     gpmodels[ld][m] are hdpgpc_b200.GPI_model objects (e.g. GPI_model.from_reference(ref_gp))."""
 
     def __init__(self, gpmodels, transTheta, startTheta, snr_norm=None, use_snr=True, device="cuda"):
+        ops._lib.require_cuda()          # fail loudly: there is no CPU path
         self.gpmodels = gpmodels
         self.n_outputs = len(gpmodels)
         self.M = len(gpmodels[0])

@@ -73,6 +73,7 @@ class _Appended:
 class GPI_model:
     def __init__(self, x_basis, f_star, f_star_sm, C, Sigma, indexes, estimation_limit=None,
                  A=None, Gamma=None, cov_f_sm=None, cov_f=None, kernel=None, device="cuda"):
+        ops._lib.require_cuda()          # fail loudly: there is no CPU path
         self.device = torch.device(device)
         self.x_basis = np.asarray(x_basis, dtype=np.float64).reshape(-1)
         self.T = self.x_basis.shape[0]
