@@ -72,6 +72,9 @@ namespace {
 __global__ void __launch_bounds__(LA_THREADS)
 chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
     __shared__ LaSmem sm;
+    extern __shared__ double la_dyn[];
+    if (threadIdx.x == 0) sm.big = T <= LA_SMEM_T ? la_dyn : nullptr;
+    __syncthreads();
     const hgp_chain_desc d = descs[blockIdx.x];
     const int n = T * T;
     const int64_t tt = (int64_t)T * T;
@@ -230,6 +233,9 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
 __global__ void __launch_bounds__(LA_THREADS)
 la_op_kernel(int op, double* A, double* B, double* C, int* piv, int T, int* info) {
     __shared__ LaSmem sm;
+    extern __shared__ double la_dyn[];
+    if (threadIdx.x == 0) sm.big = T <= LA_SMEM_T ? la_dyn : nullptr;
+    __syncthreads();
     int rc = 0;
     switch (op) {
         case 0: la_gemm(C, A, 0, B, 0, T, 1.0, 0.0, nullptr, sm); break;
@@ -255,14 +261,24 @@ extern "C" int64_t hgp_chain_work_doubles(int T) { return 8 * (int64_t)T * T + 8
 extern "C" int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream) {
     HGP_REQUIRE(n_chains >= 0 && T > 0 && T <= 1024, "hgp_chain_run: bad sizes");
     if (n_chains == 0) return 0;
-    chain_kernel<<<n_chains, LA_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const hgp_chain_desc*>(descs_device), T);
+    const size_t dyn = la_dynamic_smem_bytes(T);
+    if (dyn > 0) {
+        cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_chain_run: shared memory");
+    }
+    chain_kernel<<<n_chains, LA_THREADS, dyn, (cudaStream_t)stream>>>(reinterpret_cast<const hgp_chain_desc*>(descs_device), T);
     HGP_LAUNCH_CHECK("hgp_chain_run");
     return 0;
 }
 
 extern "C" int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream) {
     HGP_REQUIRE(T > 0 && T <= 1024, "hgp_la_op: bad T");
-    la_op_kernel<<<1, LA_THREADS, 0, (cudaStream_t)stream>>>(op, A, B, C, piv, T, info);
+    const size_t dyn = la_dynamic_smem_bytes(T);
+    if (dyn > 0) {
+        cudaError_t e = cudaFuncSetAttribute(la_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_la_op: shared memory");
+    }
+    la_op_kernel<<<1, LA_THREADS, dyn, (cudaStream_t)stream>>>(op, A, B, C, piv, T, info);
     HGP_LAUNCH_CHECK("hgp_la_op");
     return 0;
 }
@@ -286,6 +302,7 @@ pred_dist_kernel(const double* __restrict__ x_basis, int nb, const double* __res
                  double* __restrict__ fout, double* __restrict__ covout, double* __restrict__ work, int* __restrict__ info) {
     __shared__ LaSmem sm;
     __shared__ int s_const;
+    if (threadIdx.x == 0) sm.big = nullptr;
     const int64_t it = blockIdx.x;
     const int D = max(nb, nx);
     const int64_t dd = (int64_t)D * D;

@@ -18,7 +18,15 @@ struct LaSmem {
     double red[LA_THREADS / 32 + 8];
     int ipiv[LA_NB];
     int flag;
+    double* big;                   // optional dynamic shared memory: 2 x T x T doubles when T <= LA_SMEM_T, else null
 };
+
+// Matrices up to this size are factorised / solved inside shared memory (the MIT-BIH shape is T = 90): a column step of
+// the pivoted LU then costs shared-memory latencies instead of L2 round trips.
+constexpr int LA_SMEM_T = 96;
+__host__ __device__ inline size_t la_dynamic_smem_bytes(int T) {
+    return T <= LA_SMEM_T ? 2 * (size_t)T * T * sizeof(double) : 0;
+}
 
 // ---- elementwise ------------------------------------------------------------------------------
 __device__ __forceinline__ void la_copy(double* __restrict__ D, const double* __restrict__ S, int n) {
@@ -427,8 +435,23 @@ static __device__ __noinline__ void la_lu_factor_small(double* A, int* piv, int 
 //   * the 16 row interchanges are applied to the columns outside the panel, one thread per column;
 //   * U12 = L11^{-1} A12 (unit lower 16 x 16 block in shared memory, one thread per column);
 //   * A22 -= L21 U12 on the tensor cores (la_rows_update, one call per 64-row block).
+static __device__ __noinline__ void la_lu_factor_blocked(double* A, int* piv, int T, LaSmem& sm);
 static __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaSmem& sm) {
+    if (T <= LA_SMEM_T && sm.big) {
+        // small matrix: stage it in shared memory and run the blocked algorithm there (generic pointers): the panel
+        // warp and the trailing update then pay shared-memory latencies instead of L2 round trips
+        double* S = sm.big;
+        for (int i = threadIdx.x; i < T * T; i += LA_THREADS) S[i] = A[i];
+        __syncthreads();
+        la_lu_factor_blocked(S, piv, T, sm);
+        for (int i = threadIdx.x; i < T * T; i += LA_THREADS) A[i] = S[i];
+        __syncthreads();
+        return;
+    }
     if (T < LA_LU_BLOCKED_MIN) { la_lu_factor_small(A, piv, T, sm); return; }
+    la_lu_factor_blocked(A, piv, T, sm);
+}
+static __device__ __noinline__ void la_lu_factor_blocked(double* A, int* piv, int T, LaSmem& sm) {
     const int tid = threadIdx.x, lane = tid & 31;
     for (int k0 = 0; k0 < T; k0 += LA_NB) {
         const int nb = min(LA_NB, T - k0), k1 = k0 + nb;
@@ -501,6 +524,23 @@ static __device__ __noinline__ void la_lu_factor(double* A, int* piv, int T, LaS
 // B <- A^{-1} B using the factorization above (B: T x T, in place)
 static __device__ __noinline__ void la_lu_solve(const double* __restrict__ LU, const int* __restrict__ piv, double* B, int T, LaSmem& sm) {
     const int tid = threadIdx.x;
+    if (T <= LA_SMEM_T && sm.big) {
+        double* SL = sm.big;
+        double* SB = sm.big + (size_t)T * T;
+        for (int i = tid; i < T * T; i += LA_THREADS) { SL[i] = LU[i]; SB[i] = B[i]; }
+        __syncthreads();
+        for (int c = tid; c < T; c += LA_THREADS)
+            for (int k = 0; k < T; ++k) {
+                const int p = piv[k];
+                if (p != k) { const double t = SB[k * T + c]; SB[k * T + c] = SB[p * T + c]; SB[p * T + c] = t; }
+            }
+        __syncthreads();
+        la_trsm_blocked(SL, SB, T, 2, sm);     // unit lower
+        la_trsm_blocked(SL, SB, T, 3, sm);     // upper
+        for (int i = tid; i < T * T; i += LA_THREADS) B[i] = SB[i];
+        __syncthreads();
+        return;
+    }
     for (int k = 0; k < T; ++k) {   // apply the row interchanges
         const int p = piv[k];
         if (p != k)

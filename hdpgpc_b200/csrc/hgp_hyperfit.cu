@@ -35,6 +35,7 @@ hyperfit_kernel(const double* __restrict__ x, const double* __restrict__ Y, int 
     __shared__ double s_raw[4], s_m[4], s_v[4], s_hist[11];
     __shared__ int s_stop, s_count;
     const int tid = threadIdx.x;
+    if (tid == 0) sm.big = nullptr;
     const int64_t fit = blockIdx.x;
     const int64_t tt = (int64_t)T * T;
     double* E = work + fit * (3 * tt + 2 * T);   // exp(-0.5 d^2 / l^2)
