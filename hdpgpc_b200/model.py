@@ -375,6 +375,25 @@ class GPI_model:
         out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals
         return out
 
+    # ---- state export ------------------------------------------------------------------------------
+    def to_reference_lists(self):
+        """The device-resident state in the reference's own form: Python lists of CPU float64 tensors, (T, 1) column
+        vectors for means and (T, T) matrices (GPI_model.py:35-47), plus `indexes` and `N` -- what `save_swgp`
+        (GPI_HDP.py:3946-3950), `gpmodel_deepcopy` (:4037-4064) and the plotting helpers (util_plots.py:269-299) read."""
+        col = lambda t: [t[i].detach().cpu().reshape(-1, 1).clone() for i in range(t.shape[0])]
+        mat = lambda t: [] if t is None else [t[i].detach().cpu().clone() for i in range(t.shape[0])]
+        return dict(f_star=col(self.f_star), f_star_sm=col(self.f_star_sm), cov_f=mat(self.cov_f),
+                    cov_f_sm=mat(self.cov_f_sm), A=mat(self.A), Gamma=mat(self.Gamma), C=mat(self.C), Sigma=mat(self.Sigma),
+                    indexes=list(self.indexes), N=self.N, x_basis=torch.from_numpy(self.x_basis.copy()).reshape(-1, 1),
+                    kernel=self.kernel)
+
+    def adopt_into(self, ref_gp):
+        """Write the exported lists into a reference GPI_model object (attribute names are the reference's)."""
+        for k, v in self.to_reference_lists().items():
+            if k not in ("kernel", "x_basis"):
+                setattr(ref_gp, k, v)
+        return ref_gp
+
     # ---- ELBO term of the LDS parameters -----------------------------------------------------------
     def _prior_defaults(self):
         """(A_def, Gamma_def, C_def, Sigma_def): the prior the chain started from (GPI_model.py:466)."""

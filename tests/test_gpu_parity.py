@@ -483,6 +483,28 @@ def test_snr_ini_and_elbo_mirror(golden, name):
     assert np.max(np.abs(w2.cpu().numpy() - z2["ini2_snr_norm"])) < 1e-10
 
 
+def test_state_export_round_trip(golden):
+    """to_reference_lists: the reference's list-of-tensors form (shapes and values), and a model rebuilt from the exported
+    lists scores identically (save_swgp / deepcopy / plots keep working on device-resident state)."""
+    import hdpgpc_b200 as hb
+    z = golden("offline_rec100_T30_L1")
+    gp = hb.GPI_model.from_dump(z, "gp_0_0_")
+    ex = gp.to_reference_lists()
+    T = z["x_basis"].shape[0]
+    assert len(ex["f_star"]) == z["gp_0_0_f_star"].shape[0] and ex["f_star"][0].shape == (T, 1)
+    assert ex["Sigma"][-1].shape == (T, T) and ex["Sigma"][-1].device.type == "cpu" and ex["Sigma"][-1].dtype == torch.float64
+    assert np.array_equal(torch.stack(ex["cov_f_sm"]).numpy(), z["gp_0_0_cov_f_sm"])
+    assert ex["indexes"] == [int(i) for i in z["gp_0_0_indexes"]] and ex["N"] == int(z["gp_0_0_N"])
+
+    class Bag:
+        pass
+    ref_like = gp.adopt_into(Bag())
+    ref_like.x_basis, ref_like.estimation_limit = z["x_basis"], float(z["gp_0_0_estimation_limit"])
+    again = hb.GPI_model.from_reference(ref_like)
+    Y = z["data"]
+    assert torch.equal(again.compute_sq_err_all(None, Y[:, :, [0]]), gp.compute_sq_err_all(None, Y[:, :, [0]]))
+
+
 def test_first_state_and_explicit_index(golden):
     import hdpgpc_b200 as hb
     z = golden("offline_rec100_T30_L1")
