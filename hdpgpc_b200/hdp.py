@@ -257,10 +257,23 @@ class EStepEngine:
             torch.distributed.all_reduce(packed, group=self.group)
         return dict(Nm=Nm, transStateCount=trans, startStateCount=start, Q_em=Qem, packed=packed)
 
-    def sweep_from_host(self, Y_host, n_slices=8):
+    @staticmethod
+    def slice_bounds(N, n_slices, growth=1.0, tile=64):
+        """Tile-aligned slices of N beats whose sizes grow geometrically (growth = 1: equal slices).  Scoring a beat takes
+        several times longer than copying it over PCIe, so a slice `growth` times longer than the one before still
+        arrives under the scoring of its predecessor, while the exposed copy of the first slice shrinks."""
+        tiles = -(-N // tile)
+        n_slices = max(1, min(int(n_slices), tiles))
+        w = np.cumsum([float(growth) ** k for k in range(n_slices)])
+        cuts = sorted({min(tiles, max(1, int(round(tiles * c / w[-1])))) for c in w[:-1]} | {tiles})
+        edges = [0] + [min(N, c * tile) for c in cuts]
+        return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+    def sweep_from_host(self, Y_host, n_slices=4, growth=4.0):
         """The end-to-end public call: beats arrive in host memory (pinned for an asynchronous copy) in the reference's
         [N, T, L] layout (tests/test_offline.py:31), labels and statistics go back to the host.  The beats are cut into
-        tile-aligned slices; the host-to-device copy of slice k+1 runs on a copy stream under the scoring of slice k."""
+        tile-aligned slices (`slice_bounds`); the host-to-device copy of slice k+1 runs on a copy stream under the
+        scoring of slice k."""
         N, L, T = self.N, self.L, self.leads[0].T
         if tuple(Y_host.shape) != (N, T, L):
             raise HgpError(f"sweep_from_host: expected beats of shape {(N, T, L)}, got {tuple(Y_host.shape)}")
@@ -273,8 +286,7 @@ class EStepEngine:
             self._Yp = torch.empty((L, N, T), dtype=F64, device=dev)
         for ld, tb in enumerate(self.leads):
             tb.Y = self._Yp[ld]
-        per = max(64, -(-N // (n_slices * 64)) * 64)
-        bounds = [(n0, min(N, n0 + per)) for n0 in range(0, N, per)]
+        bounds = self.slice_bounds(N, n_slices, growth)
         main = torch.cuda.current_stream()
         self._copy_stream.wait_stream(main)          # earlier sweeps are done with the staging buffer
         events = []

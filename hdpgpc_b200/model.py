@@ -344,35 +344,53 @@ class GPI_model:
                             torch.from_numpy(fos).to(dev))
         return q[0, 0]
 
+    def _qlat_dirty(self, first_member):
+        """Members >= first_member score against inputs that have changed since the last compute_q_lat_all."""
+        self._qlat_stable = max(0, min(getattr(self, "_qlat_stable", 0), int(first_member)))
+
+    def invalidate_caches(self):
+        """Call after editing the histories in place from outside the model's own methods."""
+        self._tables = None
+        self._qlat_stable = 0
+
     def compute_q_lat_all(self, x_trains, h_ini=1.0):
         """GPI_model.compute_q_lat_all (GPI_model.py:549-559) -> log_lat_error (:288-323): per member j the
-        latent transition score of its smoothed state under (A, Gamma) of step j+1; zero elsewhere."""
+        latent transition score of its smoothed state under (A, Gamma) of step j+1; zero elsewhere.
+
+        Incremental on the online path: member j reads the smoothed states j, j+1 and the parameter
+        set min(j+1, last), so after include_weighted_sample / backwards_pair / bayesian_new_params only member 0 (it
+        reads the LAST parameter set) and the trailing members see changed inputs.  The methods that rewrite histories
+        mark the first stale member (`_qlat_dirty`); the others keep their stored value, which is what the reference's
+        O(t) recomputation (GPI_HDP.py:1972) would return for them."""
         n = x_trains.shape[0] if hasattr(x_trains, "shape") else len(x_trains)
         out = torch.zeros(n, dtype=F64, device=self.device)
         if self.N == 0 or self.Gamma is None or not bool(torch.any(self.Gamma[-1] != 0)):
             return out
         nG = self.Gamma.shape[0]
         J = self.N
-        a_idx = np.empty(J, dtype=np.int32); p_idx = np.empty(J, dtype=np.int32)
-        fp_idx = np.empty(J, dtype=np.int32); fc_idx = np.empty(J, dtype=np.int32)
-        scale = np.ones(J)
-        for j in range(J):
-            if j == 0:
-                p_idx[j] = fp_idx[j] = 1
-                a_idx[j] = nG - 1
-                scale[j] = h_ini
-            else:
-                p_idx[j] = fp_idx[j] = j
-                a_idx[j] = j + 1 if j + 1 < nG else nG - 1
-            fc_idx[j] = j + 1
         dev = self.device
+        vals = getattr(self, "_qlat_vals", None)
+        stable = min(getattr(self, "_qlat_stable", 0), J) if vals is not None else 0
+        if vals is None or vals.numel() < J:
+            grown = torch.zeros(max(J, 2 * (vals.numel() if vals is not None else 0), 8), dtype=F64, device=dev)
+            if stable:
+                grown[:stable] = vals[:stable]
+            vals = self._qlat_vals = grown
+        todo = np.concatenate([[0], np.arange(max(1, stable), J)]).astype(np.int64)
+        p_idx = np.where(todo == 0, 1, todo).astype(np.int32)
+        a_idx = np.where((todo == 0) | (todo + 1 >= nG), nG - 1, todo + 1).astype(np.int32)
+        fc_idx = (todo + 1).astype(np.int32)
+        scale = np.where(todo == 0, float(h_ini), 1.0)
         t = lambda a, dt=torch.int32: torch.from_numpy(a).to(dev).to(dt)
-        vals, info = ops.qlat_batched(self.A, self.Gamma, self.cov_f_sm, self.f_star_sm, t(a_idx), t(a_idx), t(p_idx),
-                                      t(fp_idx), t(fc_idx), gamma_scale=t(scale, F64))
+        new, info = ops.qlat_batched(self.A, self.Gamma, self.cov_f_sm, self.f_star_sm, t(a_idx), t(a_idx), t(p_idx),
+                                     t(p_idx), t(fc_idx), gamma_scale=t(scale, F64))
         bad = torch.nonzero(info).flatten()
         if bad.numel():
-            raise LinAlgError(f"linalg.cholesky: Gamma of member {int(bad[0])} is not positive-definite")
-        out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals
+            self._qlat_stable = 0
+            raise LinAlgError(f"linalg.cholesky: Gamma of member {int(todo[int(bad[0])])} is not positive-definite")
+        vals[t(todo, torch.long)] = new
+        self._qlat_stable = J
+        out[torch.as_tensor(self.indexes, device=dev, dtype=torch.long)] = vals[:J]
         return out
 
     # ---- state export (SURVEY 8f row 4) ------------------------------------------------------------------------------
@@ -543,6 +561,7 @@ class GPI_model:
         if len(self.indexes) > 1 and h == 1.0:
             ops.chain_run([self._online_desc(self._last_y, 2, self.N - 1)], self.T)
             self._tables = None
+            self._qlat_dirty(self.N - 2)       # smoothed states N-1 and N were rewritten
 
     def bayesian_new_params(self, h, model_type="dynamic", full_data=False, q=None, force=False, snr=1.0):
         """GPI_model.bayesian_new_params (:966-1115), 1-step dynamic form: MNIW update of (A, Gamma) from the last two
@@ -561,6 +580,7 @@ class GPI_model:
         for k in self._PAR:
             setattr(self, k, self._store[k][:n_par])
         self._tables = None
+        self._qlat_dirty(nC - 2)               # members that read "the last parameter set" now read another one
 
     # ---- chain replay -------------------------------------------------------------------------------
     @classmethod
@@ -600,7 +620,7 @@ class GPI_model:
         self.cov_f_sm = K[None].clone()
         self.ini_cov_is_prior = True
         self.fitted = True
-        self._tables = None
+        self.invalidate_caches()
 
     def fit_kernel_params(self, x_train, y):
         """GPI_model.fit_kernel_params (:207-241): hyper-fit on one beat (device, see csrc/hgp_hyperfit.cu); keeps the
@@ -659,7 +679,7 @@ class GPI_model:
         self.observation = {k[4:]: desc[k] for k in ("obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0")}
         self.indexes = [int(i) for i in desc["member_beats"].cpu()]
         self.N = desc["n_members"]
-        self._tables = None
+        self.invalidate_caches()
 
     def full_pass_weighted(self, x_trains, y_trains, resp, q=None, q_lat=None, snr=None):
         """GPI_model.full_pass_weighted (GPI_model.py:377-406) for a fresh fitted dynamic model: assimilate the

@@ -459,6 +459,54 @@ def test_online_seam_steps_vs_reference(golden):
     assert rel(seed2.compute_sq_err_all(None, Y[:, :, None]), z["seed_q"]) < 1e-5
 
 
+def test_online_q_lat_is_incremental(golden):
+    """compute_q_lat_all on the online path: called after every seam call of three assimilated beats it
+    re-scores only member 0 and the trailing members, and returns bitwise what a from-scratch evaluation returns (the
+    reference recomputes every member for every beat, GPI_HDP.py:1972); the final values are the reference's."""
+    import hdpgpc_b200 as hb
+    from hdpgpc_b200 import ops
+    z = golden("online_steps_T30")
+    Y = z["data"][:, :, 0]
+    gp = hb.GPI_model.from_dump(z, "pre_")
+    scored = []
+    real = ops.qlat_batched
+
+    def counting(*a, **k):
+        scored.append(int(a[4].numel()))
+        return real(*a, **k)
+
+    def check():
+        inc = gp.compute_q_lat_all(Y)
+        n_inc = scored[-1]
+        stable = gp._qlat_stable
+        gp._qlat_stable = 0
+        full = gp.compute_q_lat_all(Y, h_ini=1.0)
+        assert scored[-1] == gp.N and torch.equal(inc, full)
+        assert gp._qlat_stable == stable == gp.N
+        return n_inc
+
+    ops.qlat_batched = counting
+    try:
+        assert check() == gp.N                      # nothing cached yet
+        assert check() == 1                         # unchanged chain: member 0 only
+        for n in z["beats"]:
+            gp.include_weighted_sample(int(n), None, None, Y[n], 1.0)
+            assert check() == 2                     # the new member (+ member 0)
+            gp.backwards_pair(1.0)
+            assert check() == 3                     # states N-1, N rewritten: members N-2, N-1
+            gp.bayesian_new_params(1.0)
+            assert check() <= 4
+        ql = gp.compute_q_lat_all(Y)
+        assert scored[-1] == 1
+        h2 = gp.compute_q_lat_all(Y, h_ini=0.5)     # h_ini only enters member 0, which is never cached
+        gp._qlat_stable = 0
+        assert torch.equal(h2, gp.compute_q_lat_all(Y, h_ini=0.5))
+    finally:
+        ops.qlat_batched = real
+    nzm = z["post_q_lat"] != 0
+    assert rel(ql[cu(nzm, torch.bool)], z["post_q_lat"][nzm]) < TOL
+
+
 @pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2"])
 def test_snr_ini_and_elbo_mirror(golden, name):
     """GPI_HDP.compute_snr_ini (GPI_HDP.py:715-730), normalize_snr (:750-756) and full_LDS_elbo (:1838-1864) of the
