@@ -81,7 +81,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     T, L, M = CFG["T"], CFG["L"], CFG["M"]
-    n = args.cpu_beats
+    # a bounded sample per step: ~12 s of host work at the default, shrunk so that K steps still end within a few minutes
+    n = max(1024, min(args.cpu_beats, (10 * args.cpu_beats // max(1, args.steps)) // 64 * 64))
     for _ in range(max(args.warmup, 0) and 1):
         cpu_sweep_beats_per_s(min(n, 256), T, L, M, steps=1)
     bps, cores, times = cpu_sweep_beats_per_s(n, T, L, M, steps=max(1, args.steps))
@@ -338,7 +339,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--beats", type=int, default=0, help="beats per GPU (default: the cfg4 100000)")
-    ap.add_argument("--cpu-beats", type=int, default=2048, help="beats in the bounded CPU sample")
+    ap.add_argument("--cpu-beats", type=int, default=8192, help="beats in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-peak", action="store_true")
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"])

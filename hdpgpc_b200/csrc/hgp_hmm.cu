@@ -66,7 +66,10 @@ lead_weights_kernel(const double* __restrict__ q, const double* __restrict__ snr
 // ------------------------------------------------------------------------------------------
 // chunked exact scan
 // ------------------------------------------------------------------------------------------
-constexpr int CHUNK = 256;   // beats per chunk
+#ifndef HGP_HMM_CHUNK
+#define HGP_HMM_CHUNK 256
+#endif
+constexpr int CHUNK = HGP_HMM_CHUNK;   // beats per chunk
 
 // One CTA per chunk, 4*KP threads: thread (k = tid/4, p = tid%4) owns elements [p*KP/4, (p+1)*KP/4)
 // of row k of the transition operand in registers.
