@@ -81,7 +81,7 @@ hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __
                 double* __restrict__ ends_out, int* __restrict__ changed, int repair, int rebase) {
     constexpr int SEG = KP / 4;
     constexpr int NW = (4 * KP + 31) / 32;
-    __shared__ double s_prev[KP];      // forward: alpha_{t-1};  backward: u_{t+1} = beta_{t+1} * e_{t+1}
+    __shared__ __align__(16) double s_prev[KP];      // forward: alpha_{t-1};  backward: u_{t+1} = beta_{t+1} * e_{t+1}
     __shared__ double s_wsum[NW];
     const int tid = threadIdx.x;
     const int k = tid >> 2, p = tid & 3;
@@ -90,11 +90,22 @@ hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __
     const int64_t c = blockIdx.x;
     const int64_t t0 = c * CHUNK, t1 = hgp_min64(N, t0 + CHUNK);
 
+    // The four p lanes of a row read s_prev segments that lie SEG * 8 bytes apart -- the same banks -- and a 16-byte
+    // shared load is served a quarter-warp (two rows x four segments) at a time: read in segment order every load costs
+    // four wavefronts per quarter-warp and the scan is bound by the shared-memory pipe (ncu: 16-way conflict on every
+    // LDS.128, short-scoreboard stalls on 12 of 19 cycles per issue).  Lane p therefore walks its segment in the order
+    // c ^ p (16-byte chunks), which puts the four lanes in different banks; `row` is stored in the same order.
+    constexpr int NCH = SEG / 2;                         // 16-byte chunks per segment
+    constexpr int SKEW = (NCH >= 4) ? (NCH - 1) : 0;
     double row[SEG];
 #pragma unroll
-    for (int j = 0; j < SEG; ++j) {
-        const int col = p * SEG + j;
-        row[j] = (k < K && col < K) ? Mat[(int64_t)k * K + col] : 0.0;
+    for (int c = 0; c < NCH; ++c) {
+        const int cc = c ^ (p & SKEW);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int col = p * SEG + 2 * cc + h;
+            row[2 * c + h] = (k < K && col < K) ? Mat[(int64_t)k * K + col] : 0.0;
+        }
     }
 
     // the chunk whose start is exact by construction
@@ -149,9 +160,15 @@ hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __
             v = BACKWARD ? 1.0 : s_prev[k < KP ? k : 0] * e_t;
             if (k >= K) v = 0.0;
         } else {
-            double part = 0.0;
+            double part = 0.0, part1 = 0.0;              // two chains: the matvec is a latency chain of DFMAs
+            const double2* sp = reinterpret_cast<const double2*>(s_prev + p * SEG);
 #pragma unroll
-            for (int j = 0; j < SEG; ++j) part += row[j] * s_prev[p * SEG + j];
+            for (int c = 0; c < NCH; ++c) {
+                const double2 pv = sp[c ^ (p & SKEW)];
+                part += row[2 * c] * pv.x;
+                part1 += row[2 * c + 1] * pv.y;
+            }
+            part += part1;
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             v = BACKWARD ? part : part * e_t;
@@ -166,7 +183,9 @@ hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __
             tot = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) tot += s_wsum[w];
-            v = v / tot;
+            // reciprocal + multiply: v is often far below 1e-37 (peaked responsibilities), which sends the IEEE
+            // division of v / tot down its slow path on every step; tot itself is O(1)
+            v = v * (1.0 / tot);
         } else {
             __syncthreads();
         }

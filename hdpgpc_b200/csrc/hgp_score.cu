@@ -792,6 +792,14 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
         for (int r = n_rows + tid; r < NROW; r += 256) { row_s[r] = -1; row_m[r] = -1; }
         __syncthreads();
 
+        // the next tile's beats start their way into L2 under this tile's product
+        if (tile + gridDim.x < n_tiles) {
+            const int64_t nn0 = (tile + gridDim.x) * SNRM_BT;
+            const char* nxt = reinterpret_cast<const char*>(Y + nn0 * T);
+            const int64_t bytes = hgp_min64(SNRM_BT, N - nn0) * (int64_t)T * 8;
+            for (int64_t o = (int64_t)tid * 128; o < bytes; o += 256 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+        }
         // ---- product: acc[j][nt] for row blocks rb = warp + 8 j
         double acc[RBW][8][2];
 #pragma unroll
@@ -805,6 +813,7 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
             const int col = g * 32 + lane;
 #pragma unroll
             for (int i = 0; i < NRB; ++i) {
+                if (8 * i >= n_rows) break;          // row blocks past the tile's rows are never multiplied
                 const int sr = row_s[warp + 8 * i];
                 pre[i] = (sr >= 0 && col < T) ? __ldg(mu_sm + (int64_t)sr * T + col) : 0.0;
             }
@@ -817,6 +826,7 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
                 double* dst = Ast + ((j * NRB) * 32 + warp * 4 + (cc & 3)) * 2 + (cc >> 2);
 #pragma unroll
                 for (int i = 0; i < NRB; ++i) {
+                    if (8 * i >= n_rows) break;
                     dst[i * 64] = pre[i];
                     rsq[i] += pre[i] * pre[i];
                 }
@@ -833,6 +843,8 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
                     for (int nt = 0; nt < 8; ++nt) b[nt] = ys[nt * 32];
 #pragma unroll
                     for (int q2 = 0; q2 < RBW; ++q2) {
+                        if (8 * (warp + 8 * q2) >= n_rows) break;        // warp-uniform: an empty row block (typically
+                                                                         // half of them: M rows + one per member in the tile)
                         const double2 a = reinterpret_cast<const double2*>(Ast)[(j * NRB + warp + 8 * q2) * 32 + lane];
 #pragma unroll
                         for (int nt = 0; nt < 8; ++nt) dmma884(acc[q2][nt][0], acc[q2][nt][1], a.x, b[nt].x);

@@ -118,6 +118,56 @@ class GPI_model:
             self.free_deg = float(z[prefix + "free_deg"]) if prefix + "free_deg" in z else 5.0
         return self
 
+    # ---- trial copies and resets of the online driver ----
+    def clone(self):
+        """GPI_HDP.gpmodel_deepcopy (GPI_HDP.py:4037-4064): an independent copy of the device-resident state (the reference
+        copies the lists and shares the immutable tensors; here the histories are cloned because online steps write them
+        in place).  The score tables and the q_lat values travel with the copy: they are functions of the state only."""
+        new = object.__new__(type(self))
+        for k, v in self.__dict__.items():
+            if k in ("_store", "_online_work"):
+                continue
+            if isinstance(v, torch.Tensor):
+                new.__dict__[k] = v.clone()
+            elif isinstance(v, dict) and k != "_tables":
+                new.__dict__[k] = {kk: (vv.clone() if isinstance(vv, torch.Tensor) else vv) for kk, vv in v.items()}
+            elif isinstance(v, list):
+                new.__dict__[k] = list(v)
+            else:
+                new.__dict__[k] = v
+        return new
+
+    __deepcopy__ = lambda self, memo: self.clone()
+
+    def reinit_GP(self, save_last=False, save_index=False):
+        """GPI_model.reinit_GP (GPI_model.py:408-434), save_last=False: the initial state again, prior covariance of the
+        fitted kernel (ini_cov_def), no members."""
+        if save_last:
+            raise HgpError("reinit_GP(save_last=True) is not built")
+        if self.kernel is None or not getattr(self, "fitted", True):
+            raise HgpError("reinit_GP needs the fitted kernel of the model (prior covariance)")
+        xb = torch.from_numpy(self.x_basis).to(self.device)
+        K = ops.rbf_kernel_matrix(xb, xb, self.kernel[0], self.kernel[1])
+        self.f_star = self.f_star[:1].clone()
+        self.f_star_sm = self.f_star.clone()
+        self.cov_f, self.cov_f_sm = K[None].clone(), K[None].clone()
+        self.ini_cov_is_prior = True
+        self.indexes, self.N = [], 0
+        self._store = {}
+        self.invalidate_caches()
+
+    def reinit_LDS(self, save_last=False, save_last_diag=False, return_likelihood=False):
+        """GPI_model.reinit_LDS (:437-456), save_last=False: default parameters, fresh MNIW priors."""
+        if save_last or return_likelihood:
+            raise HgpError("reinit_LDS(save_last=True / return_likelihood=True) is not built")
+        d = self._prior_defaults()
+        for k in self._PAR:
+            setattr(self, k, d[k][None].clone())
+        for k in ("internal", "observation"):
+            self.__dict__.pop(k, None)
+        self._store = {}
+        self.invalidate_caches()
+
     # ---- index rules (host integer work) ----
     def find_closest_lower(self, t):
         """GPI_model.find_closest_lower (GPI_model.py:584-593)."""
@@ -567,8 +617,10 @@ class GPI_model:
         """GPI_model.bayesian_new_params (:966-1115), 1-step dynamic form: MNIW update of (A, Gamma) from the last two
         smoothed means and of (C, Sigma) from (y, last smoothed mean) when 1 < N < estimation_limit, then a new
         parameter set (with the annealing terms) is appended while N < estimation_limit."""
-        if full_data or force or snr != 1.0 or model_type != "dynamic" or h != 1.0:
-            raise HgpError("bayesian_new_params: only the 1-step dynamic update with h = 1 is built")
+        if h != 1.0:
+            return                       # the reference does nothing for a beat the cluster did not take (:972)
+        if full_data or force or snr != 1.0 or model_type != "dynamic":
+            raise HgpError("bayesian_new_params: only the 1-step dynamic update is built")
         nC = self.A.shape[0]
         self._reserve(self.f_star.shape[0], nC + 1)
         desc = self._online_desc(self._last_y, 4, self.N - 1)

@@ -567,6 +567,211 @@ def online_steps():
     print(f"online_steps_T30 -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def online_trace_scenario(name, rec, n, leads, stride, free_deg=20):
+    """Seam trace of a WHOLE online fit (hdpgpc/tests/test_online.py: GPI_HDP.include_sample per beat, no warp): every
+    call the driver makes on a GPI_model -- include_weighted_sample, backwards_pair, bayesian_new_params, log_sq_error,
+    compute_q_lat_all, return_LDS_param_likelihood, reinit_GP / reinit_LDS, the trial copies of gpmodel_deepcopy and
+    estimate_new as one event -- in order, with the model it was made on and what it returned, and every HMM smoothing
+    block of variational_local_terms.  Replaying the events on device models and finding every returned number
+    reproduced means the driver takes the same birth / assignment decisions."""
+    import json
+    import hdpgpc.GPI_model as gm_mod
+    GMc = gm_mod.GPI_model
+    data, labels = load_record(rec, n, leads, stride)
+    sw, x_trains, x_basis, hyper = make_model(data, free_deg=free_deg)
+    ids, keep, events, arrays = {}, [], [], {}
+    depth = [0]
+    hmms, cur = [], {}
+
+    def gid(obj):
+        if id(obj) not in ids:
+            ids[id(obj)] = len(ids)
+            keep.append(obj)                      # keeps id() unique for the whole run
+        return ids[id(obj)]
+
+    def put(ev, **arr):
+        k = len(events)
+        for nm, v in arr.items():
+            arrays[f"e{k}_{nm}"] = npy(v)
+        events.append(ev)
+
+    def beat_of(y):
+        yv = npy(y).reshape(-1)
+        hits = [t for t in range(data.shape[0]) if np.array_equal(data[t, :, 0].reshape(-1), yv)]
+        assert len(hits) == 1, hits
+        return hits[0]
+
+    def kern(gp):
+        kp = gp.gp.kernel.get_params()
+        return [float(kp["k1__k1__constant_value"]), float(kp["k1__k2__length_scale"]), float(kp["k2__noise_level"])]
+
+    def chk(m):
+        return [float(torch.trace(m)), float(torch.linalg.norm(m))]
+
+    originals = {}
+
+    def hook(nm, record):
+        orig = originals[nm] = getattr(GMc, nm)
+
+        def f(self, *a, **k):
+            top = depth[0] == 0
+            pre = dict(fitted=bool(self.fitted), N=int(self.N)) if top else None
+            depth[0] += 1
+            try:
+                out = orig(self, *a, **k)
+            finally:
+                depth[0] -= 1
+            if top:
+                record(self, pre, out, *a, **k)
+            return out
+        setattr(GMc, nm, f)
+
+    def r_inc(self, pre, out, index, x_train, x_warped, y, h, snr=None):
+        ev = dict(op="inc", gp=gid(self), index=int(index), beat=beat_of(y), h=float(h))
+        if not pre["fitted"] and self.fitted:
+            ev["kernel"] = kern(self)
+            ev["sigma0"], ev["gamma0"] = float(self.Sigma[0][0, 0]), float(self.Gamma[0][0, 0])
+        if self.N != pre["N"]:
+            put(ev, f=self.f_star[-1].reshape(-1), cov=np.array(chk(self.cov_f[-1])))
+        else:
+            put(ev)
+
+    def r_pair(self, pre, out, h, snr=None):
+        if len(self.indexes) > 1 and h == 1.0:
+            put(dict(op="pair", gp=gid(self), h=float(h)), f=stack([v.reshape(-1) for v in self.f_star_sm[-2:]]),
+                cov=np.array([chk(v) for v in self.cov_f_sm[-2:]]))
+        else:
+            put(dict(op="pair", gp=gid(self), h=float(h)))
+
+    def r_par(self, pre, out, h, model_type="dynamic", **k):
+        assert not k, k
+        put(dict(op="par", gp=gid(self), h=float(h), model_type=model_type, lenA=len(self.A)),
+            chk=np.array([chk(self.A[-1]), chk(self.Gamma[-1]), chk(self.C[-1]), chk(self.Sigma[-1])]))
+
+    def r_lsq(self, pre, out, x_train, y, mean=None, cov=None, C=None, Sigma=None, i=None, proj=False, first=False):
+        assert mean is None and cov is None and not proj and not first
+        put(dict(op="lsq", gp=gid(self), beat=beat_of(y), i=int(i)), out=np.float64(float(out)))
+
+    def r_qlat(self, pre, out, x_trains, h_ini=1.0):
+        put(dict(op="qlat", gp=gid(self), n=int(x_trains.shape[0]), h_ini=float(h_ini)), out=out)
+
+    def r_lds(self, pre, out, first=False):
+        put(dict(op="lds", gp=gid(self), first=bool(first)), out=np.float64(float(out)))
+
+    def r_reinit_gp(self, pre, out, save_last=False, save_index=False):
+        assert not save_last
+        put(dict(op="reinit_GP", gp=gid(self)))
+
+    def r_reinit_lds(self, pre, out, save_last=False, save_last_diag=False, return_likelihood=False):
+        assert not save_last and not return_likelihood
+        put(dict(op="reinit_LDS", gp=gid(self)))
+
+    for nm, rec_ in (("include_weighted_sample", r_inc), ("backwards_pair", r_pair), ("bayesian_new_params", r_par),
+                     ("log_sq_error", r_lsq), ("compute_q_lat_all", r_qlat), ("return_LDS_param_likelihood", r_lds),
+                     ("reinit_GP", r_reinit_gp), ("reinit_LDS", r_reinit_lds)):
+        hook(nm, rec_)
+
+    orig_new, orig_copy, orig_est = sw.create_gp_default, sw.gpmodel_deepcopy, sw.estimate_new
+    orig_fwd, orig_bwd, orig_csc = sw.forward, sw.backward, sw.coupled_state_coef
+
+    def new_gp(*a, **k):
+        depth[0] += 1
+        try:
+            g = orig_new(*a, **k)
+        finally:
+            depth[0] -= 1
+        put(dict(op="new", gp=gid(g), sigma0=float(g.Sigma[0][0, 0]), gamma0=float(g.Gamma[0][0, 0]),
+                 fitted=bool(g.fitted)))
+        return g
+
+    def copy_gp(src):
+        depth[0] += 1
+        try:
+            g = orig_copy(src)
+        finally:
+            depth[0] -= 1
+        put(dict(op="copy", gp=gid(g), src=gid(src)))
+        return g
+
+    def est(t, gpmodel, x_train, y, h=1.0):
+        depth[0] += 1
+        try:
+            out = orig_est(t, gpmodel, x_train, y, h=h)
+        finally:
+            depth[0] -= 1
+        put(dict(op="est", gp=gid(gpmodel), beat=beat_of(y), h=float(h)), out=np.float64(float(out)))
+        return out
+
+    def fwd(pi, trans_A, q):
+        alpha, marg = orig_fwd(pi, trans_A, q)
+        cur.clear()
+        cur.update(pi=npy(pi).copy(), q=npy(q).copy(), transTheta=npy(sw.transTheta).copy(), alpha=npy(alpha).copy(),
+                   at=len(events), M=int(sw.M))
+        return alpha, marg
+
+    def bwd(trans_A, q, margprob):
+        beta = orig_bwd(trans_A, q, margprob)
+        if "q" in cur and cur["q"].shape == tuple(q.shape) and np.array_equal(cur["q"], npy(q)):
+            cur["beta"] = npy(beta).copy()
+        return beta
+
+    def csc(alpha, beta, trans_A, q, margprobs):
+        out = orig_csc(alpha, beta, trans_A, q, margprobs)
+        if "beta" in cur and np.array_equal(cur["q"], npy(q)):
+            lp = npy(out)
+            rec_ = dict(cur)
+            rec_["z"] = np.argmax(np.log(rec_["alpha"] * rec_["beta"]), axis=1).astype(np.int32)
+            rec_["zpair"] = np.argmax(lp.reshape(lp.shape[0], -1), axis=1).astype(np.int32)
+            hmms.append(rec_)
+            cur.clear()
+        return out
+
+    # the models the constructor made before the hooks were in place
+    for ld in range(len(leads)):
+        for g in sw.gpmodels[ld]:
+            put(dict(op="new", gp=gid(g), sigma0=float(g.Sigma[0][0, 0]), gamma0=float(g.Gamma[0][0, 0]),
+                     fitted=bool(g.fitted)))
+    sw.create_gp_default, sw.gpmodel_deepcopy, sw.estimate_new = new_gp, copy_gp, est
+    sw.forward, sw.backward, sw.coupled_state_coef = fwd, bwd, csc
+    sample_at, M_after, chosen = [], [], []
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            for i in range(data.shape[0]):
+                sample_at.append(len(events))
+                sw.include_sample(x_basis, data[i], with_warp=False)
+                M_after.append(int(sw.M))
+                chosen.append(int(sw.actual_state))
+    finally:
+        for nm, orig in originals.items():
+            setattr(GMc, nm, orig)
+    final = [[gid(g) for g in sw.gpmodels[ld]] for ld in range(len(leads))]
+    out = dict(data=data, labels=labels.astype("U1"), x_basis=x_basis, M=np.int64(sw.M),
+               events=np.array(json.dumps(events)), n_events=np.int64(len(events)), n_hmm=np.int64(len(hmms)),
+               sample_at=np.array(sample_at), M_after=np.array(M_after), chosen=np.array(chosen),
+               final_models=np.array(final), resp_assigned_last=npy(sw.resp_assigned[-1]).astype(np.int32),
+               free_deg_MNIV=np.float64(sw.free_deg_MNIV), noise_bounds=np.array(sw.kernel_def.k2.noise_level_bounds),
+               ini_sigma_def=np.float64(sw.ini_sigma_def), ini_gamma_def=np.float64(sw.ini_gamma_def), **arrays)
+    for ld in range(len(leads)):
+        for m, g in enumerate(sw.gpmodels[ld]):
+            out[f"final_{ld}_{m}_f_sm"] = stack([v.reshape(-1) for v in g.f_star_sm])
+            out[f"final_{ld}_{m}_Sigma_last"] = npy(g.Sigma[-1])
+            out[f"final_{ld}_{m}_indexes"] = np.array(g.indexes, dtype=np.int64)
+    for i, h in enumerate(hmms):
+        for k in ("pi", "q", "transTheta", "z", "zpair"):
+            out[f"h{i}_{k}"] = h[k]
+        out[f"h{i}_meta"] = np.array([h["at"], h["M"]])
+        out[f"h{i}_alpha_last"] = h["alpha"][-1]
+        out[f"h{i}_beta_first"] = h["beta"][0]
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    ops = {}
+    for e in events:
+        ops[e["op"]] = ops.get(e["op"], 0) + 1
+    print(f"{name}: M={sw.M} events={len(events)} {ops} hmm blocks={len(hmms)} chosen={chosen} "
+          f"-> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 SCENARIOS = {
     # full state dumps at T=30 (every 3rd sample of the bundled T=90 beats keeps fixtures small)
     "offline_rec100_T30_L1": lambda: offline_scenario("offline_rec100_T30_L1", "100", 40, [0], 3, 24, True),
@@ -581,6 +786,8 @@ SCENARIOS = {
     # seam traces of whole offline fits (every chain replay and HMM block of include_batch)
     "trace_rec102_T30_L2": lambda: trace_scenario("trace_rec102_T30_L2", "102", 48, [0, 1], 3),
     "trace_rec100_T90_L1": lambda: trace_scenario("trace_rec100_T90_L1", "100", 40, [0], 1, 5),
+    # seam trace of a whole online fit (include_sample per beat, test_online.py settings)
+    "online_trace_rec100_T30_L1": lambda: online_trace_scenario("online_trace_rec100_T30_L1", "100", 30, [0], 3),
 }
 
 if __name__ == "__main__":

@@ -96,3 +96,39 @@ def test_host_operands_match_oracle(golden):
     i2, f2 = og.state_index_map(25)
     assert np.array_equal(i1, i2) and np.array_equal(f1, f2)
     assert np.array_equal(model.snr_state_index(idx, 5, 25), O.snr_state_index(idx, 5, 25))
+
+
+def test_slice_bounds_cover_the_beats_tile_aligned():
+    """EStepEngine.slice_bounds (host logic of sweep_from_host): the slices partition [0, N), every cut is a multiple of the
+    tile, sizes never shrink along a geometric schedule, degenerate inputs stay sane."""
+    from hdpgpc_b200.hdp import EStepEngine
+    for N in (0, 1, 63, 64, 65, 1000, 100000, 2000000 // 8):
+        for n_slices, growth in ((1, 1.0), (8, 1.0), (4, 4.0), (3, 2.0), (40, 3.0), (10 ** 6, 1.0)):
+            b = EStepEngine.slice_bounds(N, n_slices, growth)
+            if N == 0:
+                assert b == []
+                continue
+            assert b[0][0] == 0 and b[-1][1] == N and len(b) <= max(1, n_slices)
+            assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+            assert all(lo % 64 == 0 and hi > lo for lo, hi in b)
+            if growth > 1.0 and len(b) > 2:
+                sizes = [hi - lo for lo, hi in b[:-1]]
+                assert all(s2 >= s1 for s1, s2 in zip(sizes[:-1], sizes[1:]))
+    b = EStepEngine.slice_bounds(100000, 4, 4.0)
+    assert b[0][1] - b[0][0] < 100000 // 50       # the exposed first copy is a small fraction of the batch
+
+
+def test_q_lat_stale_marks():
+    """Which members compute_q_lat_all re-scores after each online seam call (index bookkeeping only, no device):
+    member j reads smoothed states j, j+1 and parameter set min(j+1, last) (GPI_model.py:288-306)."""
+    from hdpgpc_b200.model import GPI_model
+    gp = GPI_model.__new__(GPI_model)
+    gp._qlat_stable = 12                          # a chain of 12 members, all cached
+    gp._qlat_dirty(10)                            # backwards_pair with N = 12: states 11, 12 -> members 10, 11
+    assert gp._qlat_stable == 10
+    gp._qlat_dirty(11)                            # a later, weaker mark never raises the level
+    assert gp._qlat_stable == 10
+    gp._qlat_dirty(-3)
+    assert gp._qlat_stable == 0
+    gp.invalidate_caches()
+    assert gp._qlat_stable == 0 and gp._tables is None

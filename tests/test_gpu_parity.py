@@ -900,6 +900,78 @@ def test_offline_fit_trace_replay(golden, name):
     assert n_replayed == int(z["n_chains"]) > 0 and int(z["n_hmm"]) > 0
 
 
+def test_online_fit_trace_replay(golden):
+    """Config 2 of BASELINE.json (hdpgpc/tests/test_online.py, record 100, no warp): every call the reference's online
+    driver (GPI_HDP.include_sample, GPI_HDP.py:1906-2208) made on a GPI_model while it assimilated 30 beats one by one --
+    scores of the new beat, q_lat of the whole history, trial copies (gpmodel_deepcopy + reinit_GP / reinit_LDS),
+    estimate_new, Kalman / pair-smoother / MNIW steps, MNIW ELBO terms -- replayed in order on device models, and every
+    HMM smoothing block of variational_local_terms.  Each number the driver read back is reproduced (scores 1e-8, chain
+    states 1e-7, hard assignments exactly), so the device path leads it to the same births and the same labels."""
+    import hdpgpc_b200 as hb
+    from online_replay import replay
+    z = golden("online_trace_rec100_T30_L1")
+    chk = lambda m: [float(torch.trace(m)), float(torch.linalg.norm(m))]
+    Yd = cu(z["data"][:, :, 0])
+
+    class Device:
+        def new(self, s0, g0):
+            return hb.GPI_model.unfitted(z["x_basis"], tuple(z["noise_bounds"]), s0, g0, free_deg=float(z["free_deg_MNIV"]))
+
+        def copy(self, g):
+            return g.clone()
+
+        def reinit_GP(self, g):
+            g.reinit_GP(save_last=False)
+
+        def reinit_LDS(self, g):
+            g.reinit_LDS(save_last=False)
+
+        def inc(self, g, index, y, h, kernel):
+            n0 = g.N
+            if kernel is not None and h == 1.0:
+                assert g.N == 0 and not g.fitted
+                g._set_kernel(kernel)           # the reference's fitted kernel (the hyper-fit itself is tested elsewhere)
+            g.include_weighted_sample(index, None, None, y, h)
+            if g.N == n0:
+                return None, None
+            return g.f_star[-1].cpu().numpy(), chk(g.cov_f[-1])
+
+        def pair(self, g, h):
+            g.backwards_pair(h)
+            return g.f_star_sm[-2:].cpu().numpy() if len(g.indexes) > 1 else None
+
+        def par(self, g, h):
+            g.bayesian_new_params(h)
+            return g.A.shape[0], np.array([chk(g.A[-1]), chk(g.Gamma[-1]), chk(g.C[-1]), chk(g.Sigma[-1])])
+
+        def lsq(self, g, y, i):
+            return float(g.log_sq_error(None, y, i=i))
+
+        def est(self, g, y, h):
+            return float(g.estimate_new(None, y, h))
+
+        def qlat(self, g, n, h_ini):
+            return g.compute_q_lat_all(Yd[:n], h_ini=h_ini).cpu().numpy()
+
+        def lds(self, g):
+            return float(g.return_LDS_param_likelihood(first=False))
+
+        def final(self, g):
+            return g.f_star_sm.cpu().numpy(), g.Sigma[-1].cpu().numpy(), g.indexes
+
+    worst = replay(z, Device(), tol_score=1e-8, tol_state=1e-7)
+    assert worst["lsq"][0] == 58 and worst["est"][0] == 44 and worst["qlat"][0] > 90 and worst["lds"][0] > 200
+    dev = hb.GPI_HDP([[]], z["h0_transTheta"], np.ones(z["h0_transTheta"].shape[0]))
+    for i in range(int(z["n_hmm"])):
+        dev.transTheta = z[f"h{i}_transTheta"]
+        zz, zp = dev.hard_assignments(z[f"h{i}_pi"], z[f"h{i}_q"])
+        assert np.array_equal(zz.cpu().numpy(), z[f"h{i}_z"]), i
+        assert np.array_equal(zp.cpu().numpy(), z[f"h{i}_zpair"]), i
+        hm = dev._smooth(z[f"h{i}_pi"], cu(z[f"h{i}_q"]))
+        assert rel(hm.alpha[-1], z[f"h{i}_alpha_last"]) < TOL
+    assert int(z["n_hmm"]) > 100
+
+
 # ---------------------------------------------------------------------------------------------
 # size-independent properties at the benchmark shape
 # ---------------------------------------------------------------------------------------------

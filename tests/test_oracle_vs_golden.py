@@ -209,3 +209,74 @@ def test_oracle_replays_offline_fit_trace(golden):
         beta = O.hmm_backward(Pi, qn)
         assert np.array_equal(O.hard_resp(alpha, beta), z[f"h{i}_z"])
         assert np.array_equal(O.hard_resp_pair(alpha, beta, Pc, qn), z[f"h{i}_zpair"])
+
+
+def test_oracle_replays_online_fit_trace(golden):
+    """The seam trace of a whole ONLINE reference fit (generate_golden.py: online_trace_scenario; the loop of
+    hdpgpc/tests/test_online.py on 30 beats of record 100): every call GPI_HDP.include_sample made on a GPI_model, in order,
+    replayed on oracle models (trial copies and resets included), and every HMM block of variational_local_terms."""
+    import copy
+    from online_replay import replay
+    z = golden("online_trace_rec100_T30_L1")
+    chk = lambda m: [float(np.trace(m)), float(np.linalg.norm(m))]
+
+    class Oracle:
+        def new(self, s0, g0):
+            return O.OracleGP(z["x_basis"], (1.0, 1.2, 1.0), s0, g0, free_deg=float(z["free_deg_MNIV"]),
+                              noise_bounds=tuple(z["noise_bounds"]))
+
+        def copy(self, g):
+            return copy.deepcopy(g)
+
+        def reinit_GP(self, g):
+            g.reinit_GP()
+
+        def reinit_LDS(self, g):
+            g.reinit_LDS()
+
+        def inc(self, g, index, y, h, kernel):
+            if h != 1.0:                          # include_sample(posterior=False): nothing is stored (GPI_model.py:374)
+                return None, None
+            if g.N == 0 and not g.fitted:
+                g.fit_kernel_params(g.x_basis, y, fitted_kernel=kernel)
+            g.include_sample(index, None, y)
+            return g.f_star[-1], chk(g.cov_f[-1])
+
+        def pair(self, g, h):
+            if h == 1.0:
+                g.backwards_pair()
+            return np.stack(g.f_star_sm[-2:]) if len(g.indexes) > 1 else None
+
+        def par(self, g, h):
+            if h == 1.0:
+                g.bayesian_new_params()
+            return len(g.A), np.array([chk(g.A[-1]), chk(g.Gamma[-1]), chk(g.C[-1]), chk(g.Sigma[-1])])
+
+        def lsq(self, g, y, i):
+            return g.log_sq_error(None, y, i=i)
+
+        def est(self, g, y, h):
+            return g.estimate_new(None, y, h)
+
+        def qlat(self, g, n, h_ini):
+            return g.compute_q_lat_all(n, h_ini)
+
+        def lds(self, g):
+            return g.return_LDS_param_likelihood()
+
+        def final(self, g):
+            return np.stack(g.f_star_sm), g.Sigma[-1], g.indexes
+
+    worst = replay(z, Oracle(), tol_score=1e-9, tol_state=1e-9)
+    assert worst["lsq"][0] == 58 and worst["est"][0] == 44 and worst["inc"][0] == 74 and worst["pair"][0] == 15
+    assert int(z["M"]) == 2 and list(z["M_after"][:3]) == [1, 2, 2]
+    for i in range(int(z["n_hmm"])):
+        K = z[f"h{i}_q"].shape[1]
+        pi, PiT, Pi, Pc = O.hmm_operands(z[f"h{i}_transTheta"], z[f"h{i}_pi"], K)
+        qn = z[f"h{i}_q"]
+        alpha, _ = O.hmm_forward(pi, PiT, qn)
+        beta = O.hmm_backward(Pi, qn)
+        with np.errstate(divide="ignore"):
+            assert np.array_equal(O.hard_resp(alpha, beta), z[f"h{i}_z"]), i
+            assert np.array_equal(O.hard_resp_pair(alpha, beta, Pc, qn), z[f"h{i}_zpair"]), i
+        assert rel(alpha[-1], z[f"h{i}_alpha_last"]) < 1e-12
