@@ -472,6 +472,120 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Block path for beats longer than the tile kernel's register-resident 256 rows (256 < T <= 1024): the same product
+// z = W y - nu, one CTA per (64-beat tile, cluster) walking the row tiles of W one after the other.  A plain
+// shared-memory DMMA tile (64 x 64, K chunks of 16, the CTA tile of hgp_gemm.cuh) with the beats as the B operand read
+// straight from their row-major layout (B[k][c] = Y[n0 + c][k]), the triangular K loop cut at the row tile's diagonal,
+// and the whitened mean subtracted / squared / summed per beat in registers, so z never goes to memory.  Every
+// (tile, cluster) item is computed the same way whatever N is: a sliced sweep stays bitwise equal to the resident one.
+constexpr int SB = 64, SBK = 16, SBA_PITCH = 20, SBB_PITCH = 72;
+__global__ void __launch_bounds__(256)
+score_blocks_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ nu,
+                    const double* __restrict__ W, const int* __restrict__ state_of,
+                    const int* __restrict__ factor_of_cluster, int M, double* __restrict__ q) {
+    __shared__ double As[SB * SBA_PITCH];
+    __shared__ double Bs[SBK * SBB_PITCH];
+    __shared__ double s_col[4][SB];
+    __shared__ int s_state[SB];
+    __shared__ int s_any;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * SB;
+    const int m = blockIdx.y;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (tid < SB) {
+        const int st = (n0 + tid < N) ? state_of[(n0 + tid) * M + m] : -1;
+        s_state[tid] = st;
+        if (st >= 0) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) {                          // empty cluster (or a tile without a scored beat): q = 0 (GPI_model.py:494-495)
+        if (tid < SB && n0 + tid < N) q[(n0 + tid) * M + m] = 0.0;
+        return;
+    }
+    const double* Wm = W + (int64_t)factor_of_cluster[m] * T * T;
+    const int wm = warp >> 1, wn = warp & 1;   // warp tile: rows [16 wm, 16 wm + 16), beats [32 wn, 32 wn + 32)
+    int sc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) sc[j][e] = s_state[32 * wn + 8 * j + 2 * (lane & 3) + e];
+    double colsum[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colsum[j][0] = colsum[j][1] = 0.0;
+    const int nrt = (T + SB - 1) / SB;
+    for (int rt = 0; rt < nrt; ++rt) {
+        const int r0 = rt * SB;
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int kmax = min(T, r0 + SB);      // W is lower triangular: columns past the row tile's diagonal are zero
+        for (int k0 = 0; k0 < kmax; k0 += SBK) {
+            for (int idx = tid; idx < SB * SBK; idx += 256) {
+                const int r = idx / SBK, k = idx % SBK;
+                const int gr = r0 + r, gk = k0 + k;
+                As[r * SBA_PITCH + k] = (gr < T && gk <= gr) ? Wm[(int64_t)gr * T + gk] : 0.0;
+            }
+            for (int idx = tid; idx < SBK * SB; idx += 256) {
+                const int k = idx % SBK, c = idx / SBK;     // consecutive threads walk a beat's samples (contiguous)
+                const int gk = k0 + k;
+                const int64_t n = n0 + c;
+                Bs[k * SBB_PITCH + c] = (gk < T && n < N) ? __ldg(Y + n * T + gk) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ks = 0; ks < SBK / 4; ++ks) {
+                double a[2], bf[4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = As[(16 * wm + 8 * i + (lane >> 2)) * SBA_PITCH + 4 * ks + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * ks + (lane & 3)) * SBB_PITCH + 32 * wn + 8 * j + (lane >> 2)];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+            }
+            __syncthreads();
+        }
+        // element (row = r0 + 16 wm + 8 i + lane/4, beat = 32 wn + 8 j + 2 (lane%4) + e): z = acc - nu[state][row]
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int gr = r0 + 16 * wm + 8 * i + (lane >> 2);
+            if (gr < T) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int st = sc[j][e];
+                        if (st >= 0) {
+                            const double d = acc[i][j][e] - __ldg(nu + (int64_t)st * T + gr);
+                            colsum[j][e] += d * d;
+                        }
+                    }
+            }
+        }
+    }
+    // per-beat sum over the rows: the eight row groups of a warp (shuffles), then the four row warps (fixed order)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double r = colsum[j][e];
+            r += __shfl_xor_sync(0xffffffffu, r, 4);
+            r += __shfl_xor_sync(0xffffffffu, r, 8);
+            r += __shfl_xor_sync(0xffffffffu, r, 16);
+            if (lane < 4) s_col[wm][32 * wn + 8 * j + 2 * lane + e] = r;
+        }
+    __syncthreads();
+    if (tid < SB && n0 + tid < N) {
+        const double tot = ((s_col[0][tid] + s_col[1][tid]) + s_col[2][tid]) + s_col[3][tid];
+        q[(n0 + tid) * M + m] = (s_state[tid] >= 0) ? (-0.5 * tot - 0.5 * (double)T * HGP_LOG2PI) : 0.0;
+    }
+}
+
 // Uniform state of every (64-beat tile, cluster): the common state index if all beats of the tile (inside [0, N))
 // score against the same state of the cluster (-1 = empty cluster included), -2 otherwise.
 __global__ void tile_uniform_states_kernel(const int* __restrict__ state_of, int64_t N, int M, int64_t n_tiles,
@@ -988,6 +1102,17 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
         m_splits, n_items, n_coarse, fine, q);
     HGP_LAUNCH_CHECK("hgp_score_tiles");
     if (snr) return hgp_snr_states(Y, N, T, mu_sm, snr_state_of, M, snr, stream);
+    return 0;
+}
+
+extern "C" int hgp_score_blocks(const double* Y, int64_t N, int T, const double* nu, const double* W, const int* state_of,
+                                const int* factor_of_cluster, int M, double* q, void* stream) {
+    HGP_REQUIRE(N >= 0 && M >= 0 && T > 0, "hgp_score_blocks: bad sizes");
+    if (M > 65535) { hgp_set_error("hgp_score_blocks: M <= 65535 (got %d)", M); return HGP_E_UNSUPPORTED; }
+    if (N == 0 || M == 0) return 0;
+    const dim3 grid((unsigned)((N + SB - 1) / SB), (unsigned)M);
+    score_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, N, T, nu, W, state_of, factor_of_cluster, M, q);
+    HGP_LAUNCH_CHECK("hgp_score_blocks");
     return 0;
 }
 

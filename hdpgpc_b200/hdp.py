@@ -92,8 +92,9 @@ class LeadTables:
         self.factor_of_cluster = None
         self.pair_n = self.pair_m = None
         self.use_tiles = False
+        self.block_path = T > 256                   # beats longer than the tile kernel's 256 rows: hgp_score_blocks
         if tile_path is None:
-            tile_path = T <= 256
+            tile_path = True
         if tile_path and N > 0:
             self._plan_tiles()
 
@@ -110,9 +111,10 @@ class LeadTables:
             return  # mostly per-state covariances (estimation_limit=None regime): pair kernel for everything
         self.use_tiles = True
         self.factor_of_cluster = main_c.to(I32).contiguous()
-        self.Wpacked = ops.pack_factors(self.W)
         self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
-        self.tile_state = ops.tile_uniform_states(self.state_of)
+        if not self.block_path:
+            self.Wpacked = ops.pack_factors(self.W)
+            self.tile_state = ops.tile_uniform_states(self.state_of)
         if n_exc:
             nz = torch.nonzero(exc)
             self.pair_n = nz[:, 0].to(I32).contiguous()
@@ -122,9 +124,14 @@ class LeadTables:
         """q (and, when snr_out is given, the SNR statistic) for this lead plane."""
         if self.use_tiles:
             fuse = snr_out is not None and self.snr_state_of is not None
-            ops.score_tiles(self.Y, self.nu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out,
-                            tile_state=self.tile_state, mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of if fuse else None,
-                            snr_out=snr_out if fuse else None)
+            if self.block_path:
+                ops.score_blocks(self.Y, self.nu, self.W, self.state_of, self.factor_of_cluster, out=out)
+                if fuse:
+                    self.snr(snr_out)
+            else:
+                ops.score_tiles(self.Y, self.nu, self.Wpacked, self.state_of, self.factor_of_cluster, out=out,
+                                tile_state=self.tile_state, mu_sm=self.mu_sm if fuse else None,
+                                snr_state_of=self.snr_state_of if fuse else None, snr_out=snr_out if fuse else None)
             if self.pair_n is not None:
                 ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m,
                                 out=out)
@@ -143,6 +150,11 @@ class LeadTables:
         if not self.use_tiles or n0 % 64:
             raise HgpError("score_slice needs the tile path and a tile-aligned slice start")
         fuse = snr_out is not None and self.snr_state_of is not None
+        if self.block_path:
+            ops.score_blocks(self.Y[n0:n1], self.nu, self.W, self.state_of[n0:n1], self.factor_of_cluster, out=out[n0:n1])
+            if fuse:
+                ops.snr_states(self.Y[n0:n1], self.mu_sm, self.snr_state_of[n0:n1], out=snr_out[n0:n1])
+            return
         ops.score_tiles(self.Y[n0:n1], self.nu, self.Wpacked, self.state_of[n0:n1], self.factor_of_cluster,
                         out=out[n0:n1], tile_state=self.tile_state[n0 // 64:],
                         mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of[n0:n1] if fuse else None,
@@ -278,7 +290,7 @@ class EStepEngine:
         if tuple(Y_host.shape) != (N, T, L):
             raise HgpError(f"sweep_from_host: expected beats of shape {(N, T, L)}, got {tuple(Y_host.shape)}")
         if not all(tb.use_tiles for tb in self.leads):
-            raise HgpError("sweep_from_host needs the tile path (shared covariance per cluster, T <= 256)")
+            raise HgpError("sweep_from_host needs the tile path (one shared covariance per cluster for most beats)")
         dev = self.device
         if getattr(self, "_stage", None) is None:
             self._stage = torch.empty((N, T, L), dtype=F64, device=dev)

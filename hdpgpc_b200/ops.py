@@ -134,6 +134,18 @@ def score_tiles(Y, nu, Wpacked, state_of, factor_of_cluster, out=None, tile_stat
     return q
 
 
+def score_blocks(Y, nu, W, state_of, factor_of_cluster, out=None):
+    """Tensor-core emission scores of one lead plane for beats longer than the tile kernel's 256 samples; plain factors
+    W [F, T, T], nu = whiten_means(mu, W, factor_of_state)."""
+    lib = _lib_ready()
+    N, T = Y.shape
+    M = state_of.shape[1]
+    q = out if out is not None else torch.empty((N, M), dtype=F64, device=Y.device)
+    check(lib.hgp_score_blocks(ptr(Y), N, T, ptr(nu), ptr(W), ptr(state_of), ptr(factor_of_cluster), M, ptr(q),
+                               stream_ptr()), "hgp_score_blocks")
+    return q
+
+
 def score_pairs(Y, mu, W, state_of, factor_of_state, pair_n=None, pair_m=None, out=None):
     lib = _lib_ready()
     N, T = Y.shape

@@ -95,6 +95,11 @@ int hgp_whiten_means(const double* mu, const double* W, const int* factor_of_sta
 int hgp_score_tiles(const double* Y, int64_t N, int T, const double* nu, const double* Wpacked,
                     const int* state_of, const int* tile_state, const int* factor_of_cluster, int M, double* q,
                     const double* mu_sm, const int* snr_state_of, double* snr, void* stream);
+/* hgp_score_blocks: the same scores for beats longer than the tile kernel holds in registers (T > 256; any T works):
+ *                   plain factors W[F, T, T], f = factor_of_cluster[m], whitened means nu as above; one CTA per (64-beat
+ *                   tile, cluster), z never stored.  Same reference lines as hgp_score_tiles. */
+int hgp_score_blocks(const double* Y, int64_t N, int T, const double* nu, const double* W, const int* state_of,
+                     const int* factor_of_cluster, int M, double* q, void* stream);
 int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const double* W,
                     const int* state_of, const int* factor_of_state, int M,
                     const int* pair_n, const int* pair_m, int64_t n_pairs, double* q, void* stream);

@@ -662,7 +662,8 @@ def test_hmm_synthetic_vs_reference(golden):
 # tensor-core tile kernel vs pair kernel vs oracle on seeded synthetic workloads
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,T,L,M", [(300, 64, 2, 6), (131, 90, 1, 5), (64, 256, 1, 4), (257, 17, 2, 3), (1, 30, 1, 2),
-                                     (70, 255, 1, 9), (200, 8, 1, 2)])
+                                     (70, 255, 1, 9), (200, 8, 1, 2),
+                                     (300, 320, 1, 5), (130, 400, 2, 3), (65, 257, 1, 2)])   # T > 256: hgp_score_blocks
 def test_tiles_vs_pairs_vs_oracle(N, T, L, M):
     from hdpgpc_b200 import synthetic
     wl_cpu = synthetic.make_workload(N, T=T, L=L, M=M, seed=100 + N)
@@ -670,7 +671,7 @@ def test_tiles_vs_pairs_vs_oracle(N, T, L, M):
     wl["leads"] = [{k: v.cuda() for k, v in tb.items()} for tb in wl_cpu["leads"]]
     eng_t = synthetic.build_engine(wl, tile_path=True)
     eng_p = synthetic.build_engine(wl, tile_path=False)
-    assert eng_t.leads[0].use_tiles and not eng_p.leads[0].use_tiles
+    assert eng_t.leads[0].use_tiles and not eng_p.leads[0].use_tiles and eng_t.leads[0].block_path == (T > 256)
     out_t, out_p = eng_t.sweep(), eng_p.sweep()
     q = np.zeros((N, M, L)); snr = np.zeros((N, M, L))
     for ld, tb in enumerate(wl_cpu["leads"]):
@@ -836,11 +837,13 @@ def test_snr_tensor_core_path_vs_scalar_and_oracle(N, T, M):
         assert float(fast[n_eq, 0]) > 100.0 and abs(float(fast[n_eq, 0]) - float(want[n_eq, 0])) < 1e-6
 
 
-def test_sweep_from_host_equals_resident_sweep():
+@pytest.mark.parametrize("N,T", [(1000, 64), (300, 288)])
+def test_sweep_from_host_equals_resident_sweep(N, T):
     """The end-to-end call (pinned host beats, sliced H2D copies overlapped with scoring) gives bitwise the same scores,
-    labels and statistics as the device-resident sweep, for a beat count that is not a multiple of the slice size."""
+    labels and statistics as the device-resident sweep, for a beat count that is not a multiple of the slice size
+    (T = 288: the block path for beats longer than 256 samples)."""
     from hdpgpc_b200 import synthetic
-    N, T, L, M = 1000, 64, 2, 5
+    L, M = 2, 5
     wl = synthetic.make_workload(N, T=T, L=L, M=M, seed=21, device="cuda")
     eng = synthetic.build_engine(wl)
     ref = eng.sweep()
