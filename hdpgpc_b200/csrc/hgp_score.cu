@@ -523,19 +523,30 @@ score_blocks_kernel(const double* __restrict__ Y, int64_t N, int T, const double
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         const int kmax = min(T, r0 + SB);      // W is lower triangular: columns past the row tile's diagonal are zero
-        for (int k0 = 0; k0 < kmax; k0 += SBK) {
-            for (int idx = tid; idx < SB * SBK; idx += 256) {
+        // operands of the next K chunk travel from global memory into registers under the current chunk's DMMAs
+        double ra[4], rb[4];
+        auto gload = [&](int k0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = tid + 256 * u;
                 const int r = idx / SBK, k = idx % SBK;
                 const int gr = r0 + r, gk = k0 + k;
-                As[r * SBA_PITCH + k] = (gr < T && gk <= gr) ? Wm[(int64_t)gr * T + gk] : 0.0;
-            }
-            for (int idx = tid; idx < SBK * SB; idx += 256) {
-                const int k = idx % SBK, c = idx / SBK;     // consecutive threads walk a beat's samples (contiguous)
-                const int gk = k0 + k;
+                ra[u] = (gr < T && gk <= gr) ? __ldg(Wm + (int64_t)gr * T + gk) : 0.0;
+                const int c = idx / SBK;                     // consecutive threads walk a beat's samples (contiguous)
                 const int64_t n = n0 + c;
-                Bs[k * SBB_PITCH + c] = (gk < T && n < N) ? __ldg(Y + n * T + gk) : 0.0;
+                rb[u] = (gk < T && n < N) ? __ldg(Y + n * T + gk) : 0.0;
+            }
+        };
+        gload(0);
+        for (int k0 = 0; k0 < kmax; k0 += SBK) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = tid + 256 * u;
+                As[(idx / SBK) * SBA_PITCH + idx % SBK] = ra[u];
+                Bs[(idx % SBK) * SBB_PITCH + idx / SBK] = rb[u];
             }
             __syncthreads();
+            if (k0 + SBK < kmax) gload(k0 + SBK);
 #pragma unroll
             for (int ks = 0; ks < SBK / 4; ++ks) {
                 double a[2], bf[4];
