@@ -788,6 +788,8 @@ SCENARIOS = {
     "trace_rec100_T90_L1": lambda: trace_scenario("trace_rec100_T90_L1", "100", 40, [0], 1, 5),
     # seam trace of a whole online fit (include_sample per beat, test_online.py settings)
     "online_trace_rec100_T30_L1": lambda: online_trace_scenario("online_trace_rec100_T30_L1", "100", 30, [0], 3),
+    # ... and at the shipped beat length (T = 90)
+    "online_trace_rec100_T90_L1": lambda: online_trace_scenario("online_trace_rec100_T90_L1", "100", 24, [0], 1),
 }
 
 if __name__ == "__main__":

@@ -904,16 +904,19 @@ def test_offline_fit_trace_replay(golden, name):
     assert n_replayed == int(z["n_chains"]) > 0 and int(z["n_hmm"]) > 0
 
 
-def test_online_fit_trace_replay(golden):
+@pytest.mark.parametrize("name", ["online_trace_rec100_T30_L1", "online_trace_rec100_T90_L1"])
+def test_online_fit_trace_replay(golden, name):
     """Config 2 of BASELINE.json (hdpgpc/tests/test_online.py, record 100, no warp): every call the reference's online
-    driver (GPI_HDP.include_sample, GPI_HDP.py:1906-2208) made on a GPI_model while it assimilated 30 beats one by one --
+    driver (GPI_HDP.include_sample, GPI_HDP.py:1906-2208) made on a GPI_model while it assimilated the beats one by one
+    (30 beats at T = 30: 2 clusters; 24 beats at the shipped T = 90: 10 clusters, 2183 calls) --
     scores of the new beat, q_lat of the whole history, trial copies (gpmodel_deepcopy + reinit_GP / reinit_LDS),
     estimate_new, Kalman / pair-smoother / MNIW steps, MNIW ELBO terms -- replayed in order on device models, and every
     HMM smoothing block of variational_local_terms.  Each number the driver read back is reproduced (scores 1e-8, chain
     states 1e-7, hard assignments exactly), so the device path leads it to the same births and the same labels."""
     import hdpgpc_b200 as hb
+    import json
     from online_replay import replay
-    z = golden("online_trace_rec100_T30_L1")
+    z = golden(name)
     chk = lambda m: [float(torch.trace(m)), float(torch.linalg.norm(m))]
     Yd = cu(z["data"][:, :, 0])
 
@@ -964,7 +967,9 @@ def test_online_fit_trace_replay(golden):
             return g.f_star_sm.cpu().numpy(), g.Sigma[-1].cpu().numpy(), g.indexes
 
     worst = replay(z, Device(), tol_score=1e-8, tol_state=1e-7)
-    assert worst["lsq"][0] == 58 and worst["est"][0] == 44 and worst["qlat"][0] > 90 and worst["lds"][0] > 200
+    n_ev = lambda op: sum(1 for e in json.loads(str(z["events"])) if e["op"] == op)
+    assert worst["lsq"][0] == n_ev("lsq") > 50 and worst["est"][0] == n_ev("est") > 40 and worst["lds"][0] == n_ev("lds") > 200
+    assert worst["qlat"][0] > 90
     dev = hb.GPI_HDP([[]], z["h0_transTheta"], np.ones(z["h0_transTheta"].shape[0]))
     for i in range(int(z["n_hmm"])):
         dev.transTheta = z[f"h{i}_transTheta"]

@@ -211,13 +211,14 @@ def test_oracle_replays_offline_fit_trace(golden):
         assert np.array_equal(O.hard_resp_pair(alpha, beta, Pc, qn), z[f"h{i}_zpair"])
 
 
-def test_oracle_replays_online_fit_trace(golden):
+@pytest.mark.parametrize("name", ["online_trace_rec100_T30_L1", "online_trace_rec100_T90_L1"])
+def test_oracle_replays_online_fit_trace(golden, name):
     """The seam trace of a whole ONLINE reference fit (generate_golden.py: online_trace_scenario; the loop of
     hdpgpc/tests/test_online.py on 30 beats of record 100): every call GPI_HDP.include_sample made on a GPI_model, in order,
     replayed on oracle models (trial copies and resets included), and every HMM block of variational_local_terms."""
     import copy
     from online_replay import replay
-    z = golden("online_trace_rec100_T30_L1")
+    z = golden(name)
     chk = lambda m: [float(np.trace(m)), float(np.linalg.norm(m))]
 
     class Oracle:
@@ -268,8 +269,10 @@ def test_oracle_replays_online_fit_trace(golden):
             return np.stack(g.f_star_sm), g.Sigma[-1], g.indexes
 
     worst = replay(z, Oracle(), tol_score=1e-9, tol_state=1e-9)
-    assert worst["lsq"][0] == 58 and worst["est"][0] == 44 and worst["inc"][0] == 74 and worst["pair"][0] == 15
-    assert int(z["M"]) == 2 and list(z["M_after"][:3]) == [1, 2, 2]
+    import json
+    n_ev = lambda op: sum(1 for e in json.loads(str(z["events"])) if e["op"] == op)
+    assert worst["lsq"][0] == n_ev("lsq") > 50 and worst["est"][0] == n_ev("est") > 40 and worst["lds"][0] == n_ev("lds")
+    assert int(z["M"]) == int(z["M_after"][-1]) == {"online_trace_rec100_T30_L1": 2, "online_trace_rec100_T90_L1": 10}[name]
     for i in range(int(z["n_hmm"])):
         K = z[f"h{i}_q"].shape[1]
         pi, PiT, Pi, Pc = O.hmm_operands(z[f"h{i}_transTheta"], z[f"h{i}_pi"], K)
