@@ -424,7 +424,7 @@ def warp_scenario():
     print(f"warp_rec102_T90 -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
-def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
+def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3, warp=False):
     """Seam trace of a WHOLE offline fit: every chain replay (GPI_model.full_pass_weighted on an empty model) and every
     HMM smoothing block (forward -> backward -> coupled_state_coef -> _safe_exp) the reference's VI driver
     (GPI_HDP.include_batch, births / reallocations / accept-reject included) executes, with inputs and outputs.
@@ -432,7 +432,22 @@ def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
     decisions are taken on is reproduced, hence the same cluster assignments and cluster count."""
     data, labels = load_record(rec, n, leads, stride)
     sw, x_trains, x_basis, hyper = make_model(data, n_explore_steps=n_explore_steps)
-    GM = hdp.GPI_model.GPI_model if hasattr(hdp, "GPI_model") and hasattr(hdp.GPI_model, "GPI_model") else None
+    warps = []
+    if warp:
+        # BASELINE.json configs[2]: the offline fit with alignment enabled.  Every call of the cached all-beats driver
+        # (GPI_HDP.warp_batch_by_resp_amtgp_cached, GPI_HDP.py:3412-3517) is recorded with the representative beats it
+        # aligned against and what it returned; the chains below then run on WARPED beats, which are stored per chain.
+        orig_drv = sw.warp_batch_by_resp_amtgp_cached
+
+        def drv(x_trains=None, y_trains=None, resp_temp=None, f_ind_old=None, **k):
+            refs = sw.f_ind_old if f_ind_old is None else f_ind_old
+            out_ = orig_drv(x_trains=x_trains, y_trains=y_trains, resp_temp=resp_temp, f_ind_old=f_ind_old, **k)
+            if sw.warp:
+                Mw = int(resp_temp.shape[1])
+                warps.append(dict(refs=np.array([int(v) for v in refs][:Mw]), y_in=npy(y_trains).copy(), yw=npy(out_[0]).copy(),
+                                  xw=npy(out_[1]).copy(), liks=npy(out_[2]).copy(), n_wp=len(sw.wp_sys[0]), kw=sorted(k)))
+            return out_
+        sw.warp_batch_by_resp_amtgp_cached = drv
     import hdpgpc.GPI_model as gm_mod
     GMc = gm_mod.GPI_model
     chains, hmms = [], []
@@ -448,7 +463,7 @@ def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
         if fresh and np.count_nonzero(r > 0.99) > 0 and out[0] is not None:
             kp = self.gp.kernel.get_params()
             ld = int(np.argmin([float(torch.sum(torch.abs(y_tr[:, :, 0] - torch.from_numpy(data[:, :, l])))) for l in range(data.shape[2])]))
-            chains.append(dict(resp=(r > 0.99), lead=ld, fitted_before=fitted_before,
+            chains.append(dict(resp=(r > 0.99), lead=ld, fitted_before=fitted_before, Y=npy(y_tr[:, :, 0]).copy(),
                                kernel=np.array([kp["k1__k1__constant_value"], kp["k1__k2__length_scale"], kp["k2__noise_level"]]),
                                sigma0=float(self.Sigma[0][0, 0]), gamma0=float(self.Gamma[0][0, 0]),
                                q=npy(out[0]), q_lat=npy(out[1]), n_states=len(self.f_star),
@@ -488,7 +503,7 @@ def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
     buf = io.StringIO()
     try:
         with contextlib.redirect_stdout(buf):
-            sw.include_batch(x_trains, data)
+            sw.include_batch(x_trains, data, warp=warp)
     finally:
         GMc.full_pass_weighted = orig_fpw
     out = dict(data=data, labels=labels.astype("U1"), x_basis=x_basis, M=np.int64(sw.M),
@@ -502,6 +517,26 @@ def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
         out[f"c{i}_meta"] = np.array([c["lead"], c["fitted_before"], c["n_states"], c["sigma0"], c["gamma0"]], dtype=np.float64)
         for k in ("kernel", "q", "q_lat", "f_last", "Sig_chk"):
             out[f"c{i}_{k}"] = c[k]
+        if warp:
+            out[f"c{i}_Y"] = c["Y"]
+    if warp:
+        w0 = sw.wp_sys[0][0]
+        bw = sw.wp_sys[0][-1]
+        out.update(n_warp=np.int64(len(warps)), warp_noise=np.float64(np.sqrt(sw.ini_sigma_def)),
+                   warp_theta=np.float64(sw.kernel_def.get_params()["k1__k2__length_scale"]),
+                   warp_noise_warp=np.float64(w0.noise_warp_default), warp_noise_bounds=np.array(w0.noise_bounds, dtype=np.float64),
+                   warp_fit_noise_warp=np.array([w.warp_gp.noise_warp for w in sw.wp_sys[0]]),
+                   warp_fit_noise_bounds=np.array([w.warp_gp.noise_bounds for w in sw.wp_sys[0]], dtype=np.float64),
+                   warp_n_ctrl=np.int64(w0.n_ctrl), warp_lr=np.float64(w0.lr),
+                   warp_base_noise_warp=np.float64(bw.warp_gp.noise_warp),
+                   warp_base_noise_bounds=np.array(bw.warp_gp.noise_bounds, dtype=np.float64),
+                   warp_recursive=np.bool_(any(bool(getattr(w, "recursive", False)) for w in sw.wp_sys[0])),
+                   warp_x_basis_warp=npy(sw.x_basis_warp[0] if isinstance(sw.x_basis_warp, list) else sw.x_basis_warp))
+        for i, w in enumerate(warps):
+            assert np.array_equal(w["y_in"], data)       # the driver always aligns the original beats
+            for k in ("refs", "yw", "xw", "liks"):
+                out[f"w{i}_{k}"] = w[k]
+            out[f"w{i}_n_wp"] = np.int64(w["n_wp"])
     for i, h in enumerate(hmms):
         for k in ("pi", "q", "transTheta", "z", "zpair"):
             out[f"h{i}_{k}"] = h[k]
@@ -509,7 +544,7 @@ def trace_scenario(name, rec, n, leads, stride, n_explore_steps=3):
         out[f"h{i}_beta_first"] = h["beta"][0]
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
-    print(f"{name}: M={sw.M} chains={len(chains)} (other full_pass calls: {skipped[0]}) hmm blocks={len(hmms)} "
+    print(f"{name}: M={sw.M} chains={len(chains)} warp driver calls={len(warps)} (other full_pass calls: {skipped[0]}) hmm blocks={len(hmms)} "
           f"sizes={np.bincount(out['resp_assigned_last']).tolist()} -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
@@ -786,6 +821,8 @@ SCENARIOS = {
     # seam traces of whole offline fits (every chain replay and HMM block of include_batch)
     "trace_rec102_T30_L2": lambda: trace_scenario("trace_rec102_T30_L2", "102", 48, [0, 1], 3),
     "trace_rec100_T90_L1": lambda: trace_scenario("trace_rec100_T90_L1", "100", 40, [0], 1, 5),
+    # ... with alignment enabled (BASELINE.json configs[2]: test_offline.py 102 with warp)
+    "trace_warp_rec102_T30_L1": lambda: trace_scenario("trace_warp_rec102_T30_L1", "102", 24, [0], 3, warp=True),
     # seam trace of a whole online fit (include_sample per beat, test_online.py settings)
     "online_trace_rec100_T30_L1": lambda: online_trace_scenario("online_trace_rec100_T30_L1", "100", 30, [0], 3),
     # ... and at the shipped beat length (T = 90)

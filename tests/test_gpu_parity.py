@@ -859,7 +859,7 @@ def test_sweep_from_host_equals_resident_sweep(N, T):
 # ---------------------------------------------------------------------------------------------
 # seam trace of a whole offline fit
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["trace_rec102_T30_L2", "trace_rec100_T90_L1"])
+@pytest.mark.parametrize("name", ["trace_rec102_T30_L2", "trace_rec100_T90_L1", "trace_warp_rec102_T30_L1"])
 def test_offline_fit_trace_replay(golden, name):
     """Every chain replay and every HMM smoothing block that the reference's VI driver executed during a whole
     `include_batch` fit on MIT-BIH beats (births, reallocations and accept/reject steps included), replayed through the
@@ -877,7 +877,9 @@ def test_offline_fit_trace_replay(golden, name):
         resp = np.unpackbits(z[f"c{i}_resp"])[:N].astype(np.float64)
         lead, fitted_before, n_states, sigma0, gamma0 = z[f"c{i}_meta"]
         gp = hb.GPI_model.fresh(xb, z[f"c{i}_kernel"], float(sigma0), float(gamma0), free_deg=float(z["free_deg_MNIV"]))
-        q, ql = gp.full_pass_weighted(None, Y[:, :, [int(lead)]], resp)
+        # the fit with alignment enabled runs its chains on the WARPED beats of the cluster's representative
+        Yc = z[f"c{i}_Y"][:, :, None] if f"c{i}_Y" in z else Y[:, :, [int(lead)]]
+        q, ql = gp.full_pass_weighted(None, Yc, resp)
         # Chain replays are reproducible to ~1e-8 only: the first Kalman step solves against K + sigma^2 I with a
         # condition number ~1e7, and the numpy/LAPACK oracle itself differs from the torch/LAPACK reference by up to
         # 2.5e-8 in q and 2.1e-7 in the noise covariance on the 48-member chain of this trace (all other chains: 2e-9).
@@ -902,6 +904,30 @@ def test_offline_fit_trace_replay(golden, name):
         hm = dev._smooth(z[f"h{i}_pi"], cu(z[f"h{i}_q"]))
         assert rel(hm.alpha[-1], z[f"h{i}_alpha_last"]) < TOL
     assert n_replayed == int(z["n_chains"]) > 0 and int(z["n_hmm"]) > 0
+    if "n_warp" in z:
+        # BASELINE.json configs[2]: every call of the cached all-beats alignment driver
+        # (GPI_HDP.warp_batch_by_resp_amtgp_cached, GPI_HDP.py:3412-3517) of the whole include_batch(warp=True) fit
+        from hdpgpc_b200 import warp as hw
+        x = xb.reshape(-1)
+        Y0 = cu(Y[:, :, 0])
+        mk = lambda: hw.Warping_system(np.arange(0, T, 2.0), float(z["warp_noise_warp"]), tuple(z["warp_noise_bounds"]),
+                                       recursive=False)
+        assert mk().n_ctrl == int(z["warp_n_ctrl"]) and mk().lr == float(z["warp_lr"]) and not bool(z["warp_recursive"])
+        noise_vec = np.full(T, float(z["warp_noise"]))
+        done = {}
+        for i in range(int(z["n_warp"])):
+            refs = [int(r) for r in z[f"w{i}_refs"]]
+            key = (tuple(refs), int(z[f"w{i}_n_wp"]))
+            if key not in done:
+                ws = [mk() for _ in range(key[1])]
+                done[key] = hw.warp_batch_by_resp(cu(x), Y0, refs, ws, ws[-1], float(z["warp_theta"]), noise_vec)
+            yw, xw, liks = done[key]
+            for m in range(len(refs)):
+                rx, ry = z[f"w{i}_xw"][:, :, 0, m], z[f"w{i}_yw"][:, :, 0, m]
+                assert np.max(np.abs(xw[:, :, m].cpu().numpy() - rx)) < TOL * max(np.max(np.abs(rx)), 1e-3), (i, m)
+                assert np.max(np.abs(yw[:, :, m].cpu().numpy() - ry)) < TOL * np.max(np.abs(ry)), (i, m)
+                assert rel(liks[:, m], z[f"w{i}_liks"][:, m, 0]) < TOL, (i, m)
+        assert len(done) >= 5
 
 
 @pytest.mark.parametrize("name", ["online_trace_rec100_T30_L1", "online_trace_rec100_T90_L1"])

@@ -283,3 +283,47 @@ def test_oracle_replays_online_fit_trace(golden, name):
             assert np.array_equal(O.hard_resp(alpha, beta), z[f"h{i}_z"]), i
             assert np.array_equal(O.hard_resp_pair(alpha, beta, Pc, qn), z[f"h{i}_zpair"]), i
         assert rel(alpha[-1], z[f"h{i}_alpha_last"]) < 1e-12
+
+
+def test_oracle_replays_warp_fit_trace(golden):
+    """BASELINE.json configs[2] (offline fit with alignment enabled, record 102): every call of the cached all-beats
+    driver GPI_HDP.warp_batch_by_resp_amtgp_cached the reference made during a whole include_batch(warp=True) fit, the
+    chains on the warped beats and the HMM blocks, against the oracle."""
+    from oracle import warp_oracle as W
+    z = golden("trace_warp_rec102_T30_L1")
+    Y = z["data"][:, :, 0]
+    x = z["x_basis"].reshape(-1)
+    N, T = Y.shape
+    assert not bool(z["warp_recursive"]) and int(z["n_warp"]) > 30
+    fits = {}
+    for i in range(int(z["n_warp"])):
+        for m, ref in enumerate(z[f"w{i}_refs"]):
+            wp = min(m, int(z[f"w{i}_n_wp"]) - 1)
+            key = (int(ref), wp)
+            if key not in fits:
+                fits[key] = W.warp_all_beats(x, Y, Y[int(ref)], np.full(T, float(z["warp_noise"])),
+                                             float(z["warp_fit_noise_warp"][wp]), z["warp_fit_noise_bounds"][wp],
+                                             float(z["warp_base_noise_warp"]), z["warp_base_noise_bounds"],
+                                             theta=float(z["warp_theta"]))
+            xw, yw, lik = fits[key]
+            assert np.max(np.abs(xw - z[f"w{i}_xw"][:, :, 0, m])) < 1e-9 * max(np.max(np.abs(z[f"w{i}_xw"][:, :, 0, m])), 1e-3), (i, m)
+            assert np.max(np.abs(yw - z[f"w{i}_yw"][:, :, 0, m])) < 1e-9 * np.max(np.abs(z[f"w{i}_yw"][:, :, 0, m])), (i, m)
+            assert rel(lik, z[f"w{i}_liks"][:, m, 0]) < 1e-9, (i, m)
+    assert len(fits) >= 5
+    for i in range(0, int(z["n_chains"]), 2):
+        resp = np.unpackbits(z[f"c{i}_resp"])[:N].astype(float)
+        lead, fitted_before, n_states, s0, g0 = z[f"c{i}_meta"]
+        kern = tuple(z[f"c{i}_kernel"])
+        og = O.OracleGP(z["x_basis"], kern, float(s0), float(g0), free_deg=int(z["free_deg_MNIV"]))
+        q, ql = og.full_pass_weighted(z[f"c{i}_Y"], resp, fitted_kernel=kern)
+        assert len(og.f_star) == int(n_states)
+        assert rel(q, z[f"c{i}_q"]) < 2e-7
+    for i in range(int(z["n_hmm"])):
+        K = z[f"h{i}_q"].shape[1]
+        pi, PiT, Pi, Pc = O.hmm_operands(z[f"h{i}_transTheta"], z[f"h{i}_pi"], K)
+        qn = z[f"h{i}_q"]
+        alpha, _ = O.hmm_forward(pi, PiT, qn)
+        beta = O.hmm_backward(Pi, qn)
+        with np.errstate(divide="ignore"):
+            assert np.array_equal(O.hard_resp(alpha, beta), z[f"h{i}_z"])
+            assert np.array_equal(O.hard_resp_pair(alpha, beta, Pc, qn), z[f"h{i}_zpair"])
