@@ -94,10 +94,43 @@ class GPI_model:
     # ---- construction helpers ----
     @classmethod
     def from_reference(cls, gp, device="cuda"):
-        """gp: a reference GPI_model (or any object with the same list attributes)."""
-        return cls(gp.x_basis, gp.f_star, gp.f_star_sm, gp.C, gp.Sigma, gp.indexes,
+        """Device twin of a reference GPI_model (or any object with the same attributes): the histories, the prior
+        defaults (A_def ...), the MNIW posteriors (internal_params / observation_params, GPI_model.py:171-175), the fitted
+        kernel and the flags the chain needs.  Static models (Gamma == 0, inv_wishart observation prior) are refused."""
+        if len(gp.Gamma) and not bool(torch.any(torch.as_tensor(np.asarray(gp.Gamma[-1])) != 0)):
+            raise HgpError("static models (Gamma = 0) are outside the built path; no CPU fallback")
+        kernel = getattr(gp, "kernel", None)
+        noise_bounds = None
+        if hasattr(gp, "gp") and hasattr(gp.gp, "kernel"):
+            kp = gp.gp.kernel.get_params()
+            kernel = (float(kp["k1__k1__constant_value"]), float(kp["k1__k2__length_scale"]), float(kp["k2__noise_level"]))
+            noise_bounds = tuple(float(v) for v in gp.gp.kernel.k2.noise_level_bounds)
+        self = cls(gp.x_basis, gp.f_star, gp.f_star_sm, gp.C, gp.Sigma, gp.indexes,
                    estimation_limit=getattr(gp, "estimation_limit", None), A=gp.A, Gamma=gp.Gamma,
-                   cov_f_sm=gp.cov_f_sm, cov_f=gp.cov_f, kernel=getattr(gp, "kernel", None), device=device)
+                   cov_f_sm=gp.cov_f_sm, cov_f=gp.cov_f, kernel=kernel, device=device)
+        up = lambda t: _stack([t], self.device)[0]
+        if getattr(gp, "A_def", None) is not None:
+            self.defaults = dict(A=up(gp.A_def), Gamma=up(gp.Gamma_def), C=up(gp.C_def), Sigma=up(gp.Sigma_def))
+        for name, attr in (("internal", "internal_params"), ("observation", "observation_params")):
+            p = getattr(gp, attr, None)
+            if p is None:
+                continue
+            if not hasattr(p, "m_r_cov"):
+                raise HgpError("inverse-Wishart (static) observation priors are outside the built path")
+            setattr(self, name, dict(m_mean=up(p.m_mean).clone(), m_r_cov=up(p.m_r_cov).clone(), scale=up(p.scale).clone(),
+                                     n0=torch.tensor([float(p.n0)], dtype=F64, device=self.device)))
+        self.fitted = bool(getattr(gp, "fitted", True))
+        self.annealing = bool(getattr(gp, "annealing", True))
+        self.free_deg = float(getattr(gp, "free_deg_MNIV", 5.0))
+        if noise_bounds is not None:
+            self.noise_bounds = noise_bounds
+        if self.N == 0 and hasattr(gp, "gp") and self.cov_f_sm is not None:
+            # IterativeGaussianProcess.posterior (GPI.py:136) treats the first member specially when the prior covariance
+            # IS the kernel matrix (torch.equal on the host's own matrices); the decision travels as a flag
+            xb = np.asarray(torch.as_tensor(np.asarray(gp.x_basis)).detach().cpu(), dtype=np.float64).reshape(-1, 1)
+            K = torch.from_numpy(np.asarray(gp.gp.kernel(xb, xb), dtype=np.float64))
+            self.ini_cov_is_prior = bool(torch.equal(torch.as_tensor(np.asarray(gp.cov_f_sm[-1]), dtype=F64), K))
+        return self
 
     @classmethod
     def from_dump(cls, z, prefix, device="cuda"):
@@ -120,14 +153,20 @@ class GPI_model:
 
     # ---- trial copies and resets of the online driver ----
     def clone(self):
-        """GPI_HDP.gpmodel_deepcopy (GPI_HDP.py:4037-4064): an independent copy of the device-resident state (the reference
-        copies the lists and shares the immutable tensors; here the histories are cloned because online steps write them
-        in place).  The score tables and the q_lat values travel with the copy: they are functions of the state only."""
+        """GPI_HDP.gpmodel_deepcopy (GPI_HDP.py:4037-4064): an independent copy of the device-resident state.  Like the
+        reference (which copies the lists and shares the immutable tensors) the copy is O(1) in the history length: the
+        histories are SHARED and become copy-on-write for both parties -- the only in-place writers are the online
+        steps, which go through `_reserve`; dropping `_store` on both sides makes the next such step of either model move
+        its histories to storage of its own first.  The small in-place state (MNIW posteriors, q_lat values) is copied;
+        the score tables travel with the copy: they are functions of the state only."""
         new = object.__new__(type(self))
+        shared = set(self._HIST + self._PAR)
         for k, v in self.__dict__.items():
             if k in ("_store", "_online_work"):
                 continue
-            if isinstance(v, torch.Tensor):
+            if k in shared:
+                new.__dict__[k] = v
+            elif isinstance(v, torch.Tensor):
                 new.__dict__[k] = v.clone()
             elif isinstance(v, dict) and k != "_tables":
                 new.__dict__[k] = {kk: (vv.clone() if isinstance(vv, torch.Tensor) else vv) for kk, vv in v.items()}
@@ -135,6 +174,7 @@ class GPI_model:
                 new.__dict__[k] = list(v)
             else:
                 new.__dict__[k] = v
+        self._store = {}
         return new
 
     __deepcopy__ = lambda self, memo: self.clone()
@@ -609,6 +649,8 @@ class GPI_model:
         if snr is not None:
             raise HgpError("backwards_pair(snr=...) is not built")
         if len(self.indexes) > 1 and h == 1.0:
+            self._reserve(self.f_star.shape[0], self.A.shape[0])     # own storage first (histories may be shared)
+            self._init_mniw()
             ops.chain_run([self._online_desc(self._last_y, 2, self.N - 1)], self.T)
             self._tables = None
             self._qlat_dirty(self.N - 2)       # smoothed states N-1 and N were rewritten
@@ -623,6 +665,7 @@ class GPI_model:
             raise HgpError("bayesian_new_params: only the 1-step dynamic update is built")
         nC = self.A.shape[0]
         self._reserve(self.f_star.shape[0], nC + 1)
+        self._init_mniw()
         desc = self._online_desc(self._last_y, 4, self.N - 1)
         ops.chain_run([desc], self.T)
         fail, n_par = (int(v) for v in desc["status"])
@@ -731,6 +774,8 @@ class GPI_model:
         self.observation = {k[4:]: desc[k] for k in ("obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0")}
         self.indexes = [int(i) for i in desc["member_beats"].cpu()]
         self.N = desc["n_members"]
+        self._last_y = desc["Y"][self.indexes[-1]].reshape(1, -1).clone()      # y_train[-1] of the reference (:1029)
+        self._store = {}
         self.invalidate_caches()
 
     def full_pass_weighted(self, x_trains, y_trains, resp, q=None, q_lat=None, snr=None):
