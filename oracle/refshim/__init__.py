@@ -1,9 +1,11 @@
 """Import shims for running the UNMODIFIED reference (/root/reference) in the dev container.
 
-TEST INFRASTRUCTURE ONLY.  Used by tests/golden/generate_golden.py (run once, in the dev
-container, where /root/reference is mounted) to produce the known-answer fixtures under
-tests/golden/.  Nothing here is imported by the product package (hdpgpc_b200) and nothing
-here runs on the GPU box (the reference does not travel).
+TEST INFRASTRUCTURE ONLY.  Used by tests/golden/generate_*.py (run once, in the dev container,
+where /root/reference is mounted) to produce the known-answer fixtures under tests/golden/, and
+on the GPU box -- from the copy tools/make_ref.sh stages under oracle/_ref/ -- by the reference
+arm of bench.py and by tests/test_reference_fit_gpu.py, which drives the reference's own
+include_batch / include_sample with hdpgpc_b200.integration enabled.  Nothing here is imported
+by the product package (hdpgpc_b200).
 
 The reference imports several packages that are absent from this image:
 matplotlib, gpytorch, pyro, plotly, wfdb, torchmetrics.  They are only needed for plotting,
@@ -17,10 +19,21 @@ here, so that sub-step cannot be checked against the real library).
 """
 import importlib
 import importlib.machinery
+import os
 import sys
 import types
 
 REFERENCE_ROOT = "/root/reference/hdpgpc"
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_ref", "hdpgpc")
+
+
+def find_reference():
+    """Where the unmodified reference can be imported from: the mounted tree in the dev container, else the copy that
+    tools/make_ref.sh staged under oracle/_ref/ (git-ignored; travels to the GPU box with the gpurun snapshot)."""
+    for root in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isdir(os.path.join(root, "hdpgpc")):
+            return root
+    return None
 
 
 class _Stub(types.ModuleType):
@@ -57,9 +70,13 @@ def _stub(name):
     return m
 
 
-def install(reference_root=REFERENCE_ROOT):
+def install(reference_root=None):
     import numpy as np
     import torch
+
+    reference_root = reference_root or find_reference()
+    if reference_root is None:
+        raise ImportError("the reference package is neither mounted (/root/reference) nor staged (tools/make_ref.sh)")
 
     for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.ticker",
                  "gpytorch", "gpytorch.models", "gpytorch.variational", "gpytorch.means",
