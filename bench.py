@@ -189,7 +189,7 @@ def run_ours(args):
     B = args.beats or CFG["beats_per_gpu"]
     wl = synthetic.make_workload(B, T=T, L=L, M=M, seed=1234, device="cuda", n_offset=rank * B, N_total=world * B)
     Y_host = wl["Y"].cpu().pin_memory()                      # e2e leg: beats live in pinned host memory
-    eng = synthetic.build_engine(wl)
+    eng = synthetic.build_engine(wl, sharded=world > 1)       # rank r holds the r-th contiguous time slice
     assert all(tb.use_tiles for tb in eng.leads)
 
     if world > 1:   # a size mismatch in a broadcast hangs NCCL silently: check once, loudly

@@ -81,6 +81,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if int(lib.hgp_chain_desc_bytes()) != ctypes.sizeof(ChainDesc):
+        raise HgpError(f"hgp_chain_desc is {int(lib.hgp_chain_desc_bytes())} bytes in the library but "
+                       f"{ctypes.sizeof(ChainDesc)} in the ctypes mirror (_lib.ChainDesc): header and binding are out of step")
     _lib = lib
     return lib
 

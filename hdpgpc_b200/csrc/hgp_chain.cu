@@ -24,16 +24,20 @@ struct Mniw {
 };
 
 // matrix_normal_inv_wishart.posterior for n_k = 1 with zero covariance terms and sse_matrix = I
-// (GPI_model.py:1300-1344).  W0..W3: T x T scratch.  Returns chol info (0 = ok).
-__device__ __noinline__ int mniw_posterior_one(Mniw d, const double* y1, const double* y2, int T, double* W0, double* W1, double* W2,
-                                  double* W3, double* vec, LaSmem& sm) {
+// (GPI_model.py:1300-1344), in two halves so that a failed factorisation leaves the distribution untouched -- the
+// reference catches torch.linalg.LinAlgError around BOTH posteriors and keeps the previous parameters of both
+// (GPI_model.py:1068-1071).
+//   compute: S2 = y2 y2^T + Sinv -> W1,  part_mean^T -> W3  (W0, W2: scratch; d is only read).  Returns chol info.
+//   commit : m_mean, scale, m_r_cov, n0 updated from (W1, W3).
+__device__ __noinline__ int mniw_posterior_compute(Mniw d, const double* y1, const double* y2, int T, double* W0, double* W1,
+                                                   double* W2, double* W3, LaSmem& sm) {
     const int n = T * T;
-    const double n0 = *d.n0;
     // Ls = chol(sym(m_r_cov) + 1e-2 * max(mean|diag scale|, eps) I)
     const double jitter = 1e-2 * fmax(la_mean_abs_diag(d.scale, T, sm), HGP_EPS);
     la_copy(W0, d.m_r_cov, n);
     la_symmetrize(W0, jitter, T);
     int info = la_chol(W0, T, sm);
+    if (info) return info;                               // torch.linalg.cholesky raises here
     // Sinv = cholesky_solve(I, Ls)
     la_set_identity(W1, 1.0, T);
     la_trsm_lower(W0, W1, T, sm);
@@ -45,24 +49,30 @@ __device__ __noinline__ int mniw_posterior_one(Mniw d, const double* y1, const d
     // part_mean = cholesky_solve(S1^T, chol(sym(S2) + 1e-8 I))^T
     la_copy(W0, W1, n);
     la_symmetrize(W0, 1e-8, T);
-    int info2 = la_chol(W0, T, sm);
+    info = la_chol(W0, T, sm);
+    if (info) return info;
     la_transpose(W3, W2, T);
     la_trsm_lower(W0, W3, T, sm);
     la_trsm_lower_trans(W0, W3, T, sm);                 // W3 = part_mean^T
+    return 0;
+}
+
+__device__ __noinline__ void mniw_posterior_commit(Mniw d, const double* y1, const double* y2, int T, const double* S2,
+                                                  const double* partT) {
+    const int n = T * T;
+    const double n0 = *d.n0;
     // new_m_mean = ((n0 - 2) m_mean + part_mean) / (n0 + 1 - 2) ; new_scale = ((n0 - 2) scale + e e^T) / (n0 - 1)
     const double a = (n0 - 2.0), den = (n0 + 1.0) - 2.0;
     for (int i = threadIdx.x; i < n; i += LA_THREADS) {
         const int r = i / T, c = i % T;
-        d.m_mean[i] = (a * d.m_mean[i] + W3[(int64_t)c * T + r]) / den;
+        d.m_mean[i] = (a * d.m_mean[i] + partT[(int64_t)c * T + r]) / den;
         const double e_r = y1[r] - y2[r], e_c = y1[c] - y2[c];
         d.scale[i] = (a * d.scale[i] + e_r * e_c) / den;
-        d.m_r_cov[i] = W1[i];
+        d.m_r_cov[i] = S2[i];
     }
     __syncthreads();
     if (threadIdx.x == 0) *d.n0 = n0 + 1.0;
     __syncthreads();
-    (void)vec;
-    return info ? info : info2;
 }
 
 }  // namespace
@@ -168,9 +178,18 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
         if (N > 1 && below) {
             // the reference also factorises P = A cov_ A^T + Gamma here and discards it (:990-998); only a
             // failure of that factorization is observable (keep previous parameters) -- P is SPD by construction
-            int i1 = mniw_posterior_one(mi, d.f_star_sm + (int64_t)(s + 1) * T, d.f_star_sm + (int64_t)s * T, T, W0, W1, W2, W3, v2, sm);
-            int i2 = mniw_posterior_one(mo, y, d.f_star_sm + (int64_t)(s + 1) * T, T, W0, W1, W2, W3, v2, sm);
-            if ((i1 || i2) && !fail) fail = k + 1;
+            // both posteriors are computed before either is committed: a failure in one keeps BOTH (W4..W7 are free
+            // here: the Kalman / smoother temporaries are dead)
+            const double* f1 = d.f_star_sm + (int64_t)(s + 1) * T;
+            const double* f0 = d.f_star_sm + (int64_t)s * T;
+            const int i1 = mniw_posterior_compute(mi, f1, f0, T, W0, W1, W2, W3, sm);
+            const int i2 = i1 ? 0 : mniw_posterior_compute(mo, y, f1, T, W4, W5, W6, W7, sm);
+            if (i1 || i2) {
+                if (!fail) fail = k + 1;
+            } else {
+                mniw_posterior_commit(mi, f1, f0, T, W1, W3);
+                mniw_posterior_commit(mo, y, f1, T, W5, W7);
+            }
         }
         if (below) {
             double* An = d.A + (p + 1) * tt; double* Gn = d.Gamma + (p + 1) * tt;

@@ -46,17 +46,23 @@ lead_weights_kernel(const double* __restrict__ q, const double* __restrict__ snr
         if (wout && lane == 0)
             for (int ld = 0; ld < L; ++ld) wout[n * L + ld] = w[ld];
         double rmax = -INFINITY;
+        int has_nan = 0;
         for (int m = lane; m < M; m += 32) {
             double acc = 0.0;
             for (int ld = 0; ld < L; ++ld) acc += q[ld * plane + n * M + m] * w[ld];
             qbar[n * M + m] = acc;
-            rmax = fmax(rmax, acc);   // fmax ignores NaN like torch.max does not; NaN rows are flagged below
+            has_nan |= isnan(acc);
+            rmax = fmax(rmax, acc);
         }
         rmax = warp_max(rmax);
+        // torch.max propagates NaN (fmax does not): a row with ANY NaN score has a NaN maximum in LogLik / safe_exp
+        // (GPI_HDP.py:646, :3577), so every entry of the row becomes nan_to_num(NaN) = 1e-8.  flags bit 1 = row of NaNs.
+        has_nan = __any_sync(0xffffffffu, has_nan);
         if (lane == 0 && isinf(rmax)) atomicOr(flags, 1);
+        if (lane == 0 && has_nan) atomicOr(flags, 2);
         for (int m = lane; m < M; m += 32) {
             double v = exp(qbar[n * M + m] - rmax);
-            if (isnan(v)) v = 1e-8;                       // torch.nan_to_num(..., 1e-8)
+            if (has_nan || isnan(v)) v = 1e-8;            // torch.nan_to_num(..., 1e-8)
             else if (isinf(v)) v = 1.7976931348623157e308;
             e[n * M + m] = v;
         }

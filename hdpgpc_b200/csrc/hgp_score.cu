@@ -907,6 +907,30 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
         }
         __syncthreads();
         const int n_rows = cnt[M];
+        if (n_rows > NROW) {
+            // An arbitrary snr_state_of can change state more often down a tile than the A operand has rows (the M + 64
+            // bound only holds for the reference's rule: an index advances at the cluster's own members).  Such a tile is
+            // summed directly, one warp per pair -- block-uniform branch, nothing has been written to row_s / row_m yet.
+            for (int p = warp; p < nb * M; p += 8) {
+                const int b = p / M, m = p - b * M;
+                const int s = sstate[b * M + m];
+                double sig = 0.0, noi = 0.0;
+                if (s >= 0) {
+                    const double* mr = mu_sm + (int64_t)s * T;
+                    const double* yr = Y + (n0 + b) * T;
+                    for (int t = lane; t < T; t += 32) {
+                        const double mv = __ldg(mr + t);
+                        const double d = mv - __ldg(yr + t);
+                        sig += mv * mv;
+                        noi += d * d;
+                    }
+                }
+                sig = warp_sum(sig);
+                noi = warp_sum(noi);
+                if (lane == 0) snr[(n0 + b) * M + m] = (s >= 0) ? 10.0 * log10((sig + HGP_EPS) / (noi + HGP_EPS)) : 0.0;
+            }
+            continue;
+        }
         if (tid < M) {
             int r = cnt[tid], prev = -2;
             for (int b = 0; b < nb; ++b) {

@@ -147,7 +147,8 @@ class LeadTables:
     def score_slice(self, n0, n1, out, snr_out=None):
         """Tile-path scores (and SNR) of beats [n0, n1) only; n0 must be a multiple of the 64-beat tile.  The exception
         pairs (score_exceptions) need the whole plane and run once all slices are in."""
-        if not self.use_tiles or n0 % 64:
+        tile = ops.tile_beats()
+        if not self.use_tiles or n0 % tile:
             raise HgpError("score_slice needs the tile path and a tile-aligned slice start")
         fuse = snr_out is not None and self.snr_state_of is not None
         if self.block_path:
@@ -156,7 +157,7 @@ class LeadTables:
                 ops.snr_states(self.Y[n0:n1], self.mu_sm, self.snr_state_of[n0:n1], out=snr_out[n0:n1])
             return
         ops.score_tiles(self.Y[n0:n1], self.nu, self.Wpacked, self.state_of[n0:n1], self.factor_of_cluster,
-                        out=out[n0:n1], tile_state=self.tile_state[n0 // 64:],
+                        out=out[n0:n1], tile_state=self.tile_state[n0 // tile:],
                         mu_sm=self.mu_sm if fuse else None, snr_state_of=self.snr_state_of[n0:n1] if fuse else None,
                         snr_out=snr_out[n0:n1] if fuse else None)
 
@@ -206,14 +207,22 @@ class EStepEngine:
     HMM forward/backward -> arg-max resp / respPair -> N_m, startStateCount, transStateCount, Q_em
     (= reference cluster_new_batch(learning=False), GPI_HDP.py:2975-3001, + the count lines :890-892)."""
 
-    def __init__(self, leads, transTheta, startTheta, lead_w=None, group=None):
+    def __init__(self, leads, transTheta, startTheta, lead_w=None, group=None, sharded=None):
+        """Sharding is OPT-IN: pass `group=` (a torch.distributed process group) or `sharded=True` (the default group) when
+        the local beats are ONE CONTIGUOUS TIME SLICE of a sequence cut over the ranks in rank order.  Only then are HMM
+        boundary messages exchanged, `startStateCount` taken from rank 0 and the statistics all-reduced.  An initialised
+        process group alone changes nothing: every rank then holds (and smooths) a whole sequence of its own."""
         self.leads = leads
         self.L = len(leads)
         self.N, self.M = leads[0].N, leads[0].M
         self.device = leads[0].Y.device
         self.group = group
         self.rank, self.world = 0, 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if sharded is None:
+            sharded = group is not None
+        if sharded:
+            if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+                raise HgpError("EStepEngine(sharded=True) needs an initialised torch.distributed process group")
             self.rank = torch.distributed.get_rank(group)
             self.world = torch.distributed.get_world_size(group)
         self.lead_w = lead_w
@@ -270,10 +279,11 @@ class EStepEngine:
         return dict(Nm=Nm, transStateCount=trans, startStateCount=start, Q_em=Qem, packed=packed)
 
     @staticmethod
-    def slice_bounds(N, n_slices, growth=1.0, tile=64):
+    def slice_bounds(N, n_slices, growth=1.0, tile=None):
         """Tile-aligned slices of N beats whose sizes grow geometrically (growth = 1: equal slices).  Scoring a beat takes
         several times longer than copying it over PCIe, so a slice `growth` times longer than the one before still
         arrives under the scoring of its predecessor, while the exposed copy of the first slice shrinks."""
+        tile = tile or ops.tile_beats()
         tiles = -(-N // tile)
         n_slices = max(1, min(int(n_slices), tiles))
         w = np.cumsum([float(growth) ** k for k in range(n_slices)])

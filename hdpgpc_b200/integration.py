@@ -507,8 +507,28 @@ _PATCHES = {
 }
 
 
-def enable(gpi_model_cls=None, gpi_hdp_cls=None, igp_cls=None):
-    """Patch the reference classes (found in `hdpgpc.GPI_model` / `hdpgpc.GPI_HDP` / `hdpgpc.GPI` unless given)."""
+seam_times = {}        # "Class.method" -> [calls, seconds] (wall clock around the patched call, nested calls included)
+
+
+def _timed(key, fn):
+    import functools
+    import time
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return fn(*a, **k)
+        finally:
+            rec = seam_times.setdefault(key, [0, 0.0])
+            rec[0] += 1
+            rec[1] += time.perf_counter() - t0
+    return wrapper
+
+
+def enable(gpi_model_cls=None, gpi_hdp_cls=None, igp_cls=None, profile=False):
+    """Patch the reference classes (found in `hdpgpc.GPI_model` / `hdpgpc.GPI_HDP` / `hdpgpc.GPI` unless given).
+    profile=True accumulates calls and wall seconds per seam method in `seam_times`."""
     import importlib
     gpi_model_cls = gpi_model_cls or importlib.import_module("hdpgpc.GPI_model").GPI_model
     gpi_hdp_cls = gpi_hdp_cls or importlib.import_module("hdpgpc.GPI_HDP").GPI_HDP
@@ -519,7 +539,7 @@ def enable(gpi_model_cls=None, gpi_hdp_cls=None, igp_cls=None):
             if key not in _saved:
                 _saved[key] = getattr(cls, name)
                 _saved[key + "/cls"] = cls
-            setattr(cls, name, fn)
+            setattr(cls, name, _timed(key, fn) if profile else fn)
     return sorted(k for k in _saved if not k.endswith("/cls"))
 
 

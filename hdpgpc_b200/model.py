@@ -671,7 +671,7 @@ class GPI_model:
         fail, n_par = (int(v) for v in desc["status"])
         if fail:
             # the reference keeps the previous parameters and prints (GPI_model.py:1068-1071); the kernel already did
-            pass
+            print("Alg error matrix ill conditioned.")
         for k in self._PAR:
             setattr(self, k, self._store[k][:n_par])
         self._tables = None
@@ -766,7 +766,10 @@ class GPI_model:
     def _chain_finish(self, desc):
         fail, n_par = (int(v) for v in desc["status"])
         if fail:
-            raise LinAlgError(f"MNIW factorization failed at member {fail - 1}")
+            # torch.linalg.LinAlgError inside bayesian_new_params is caught by the reference, which prints and keeps the
+            # previous MNIW posteriors for that member (GPI_model.py:1068-1071); the kernel has done exactly that
+            print("Alg error matrix ill conditioned.")
+        self.mniw_first_failed_member = fail - 1 if fail else None
         self.f_star, self.f_star_sm = desc["f_star"], desc["f_star_sm"]
         self.cov_f, self.cov_f_sm = desc["cov_f"], desc["cov_f_sm"]
         self.A, self.Gamma, self.C, self.Sigma = (desc[k][:n_par] for k in ("A", "Gamma", "C", "Sigma"))

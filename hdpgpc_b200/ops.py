@@ -26,6 +26,11 @@ def launch_count():
     return int(_lib.load().hgp_launch_count())
 
 
+def tile_beats():
+    """Beats per tile of the tile kernel (hgp_tile_beats)."""
+    return int(_lib.load().hgp_tile_beats())
+
+
 def pack_leads(Y_ntl):
     """[N, T, L] -> [L, N, T] (reference layout -> per-lead planes)."""
     lib = _lib_ready()

@@ -145,7 +145,7 @@ def make_workload(N, T=256, L=2, M=64, seed=1234, device="cpu", n_offset=0, N_to
                 N=N, T=T, L=L, M=M)
 
 
-def build_engine(wl, group=None, tile_path=None):
+def build_engine(wl, group=None, tile_path=None, sharded=None):
     """Upload-side of the sweep: factorise the covariances with the library and assemble LeadTables."""
     from . import ops
     from .hdp import EStepEngine, LeadTables
@@ -159,4 +159,4 @@ def build_engine(wl, group=None, tile_path=None):
         W = ops.tri_inverse_batched(Lf)
         leads.append(LeadTables(Yp[ld], tb["mu"], W, tb["state_of"], tb["factor_of_state"], tb["mu_sm"],
                                 tb["snr_state_of"], tile_path=tile_path))
-    return EStepEngine(leads, wl["transTheta"], wl["startTheta"], group=group)
+    return EStepEngine(leads, wl["transTheta"], wl["startTheta"], group=group, sharded=sharded)

@@ -107,7 +107,11 @@ int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const d
 /* ---- lead weighting: GPI_HDP.compute_snr (GPI_HDP.py:732-748), weight_mean (:685-701),
  *      LogLik (:632-661) ------------------------------------------------------------------
  * snr[n*M + m] = 10 log10( (sum mu^2 + eps) / (sum (mu - y)^2 + eps) ),  mu = mu_sm[snr_state_of[n*M+m]]
- * (the smoothed latent mean f_star_sm[j], j = clip(find_closest_lower(n), 1, len-1)). */
+ * (the smoothed latent mean f_star_sm[j], j = clip(find_closest_lower(n), 1, len-1)).
+ * snr_state_of may be ANY map into mu_sm (-1 => 0).  The tensor-core path (T <= 256, M <= 128) holds one table row per
+ * run of equal states per cluster inside a 64-beat tile: 128 rows for M <= 64, 192 for M <= 128 -- always enough for the
+ * reference's rule, where an index only advances at the cluster's own members (<= M + 64 runs).  A tile with more runs
+ * is summed directly (same result, slower); nothing is ever written out of bounds. */
 int hgp_snr_states(const double* Y, int64_t N, int T, const double* mu_sm, const int* snr_state_of,
                    int M, double* snr, void* stream);
 /* Mean beat of one lead plane (GPI_HDP.compute_snr_ini, GPI_HDP.py:715-730: the SNR of every beat against the mean
@@ -119,7 +123,8 @@ int hgp_mean_beat(const double* Y, int64_t N, int T, double* mean, double* work,
  * NULL: the saved self.snr_norm), qbar[n, m] = sum_ld q[ld, n, m] w[n, ld];
  * e[n, k] = nan_to_num(exp(qn - rowmax(qn)), 1e-8) with qn = qbar - rowmax(qbar), the subtraction
  * skipped for ALL rows when any row max is +-inf (LogLik's early return, :646-648).
- * flags[0] receives that "any inf" bit.  wout (may be NULL) receives w[N, L]. */
+ * flags[0]: bit 0 = "some row maximum is +-inf", bit 1 = "some row holds a NaN score" -- torch.max propagates NaN, so
+ * every entry of such a row is nan_to_num(NaN) = 1e-8 exactly as in the reference.  wout (may be NULL) receives w[N, L]. */
 int hgp_lead_weights(const double* q, const double* snr, const double* lead_w, int64_t N, int M, int L,
                      double* qbar, double* e, double* wout, int* flags, void* stream);
 

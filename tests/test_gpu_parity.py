@@ -208,6 +208,40 @@ def test_chain_replay_vs_reference(golden, name):
                 assert np.max(np.abs(mine[-1] - ref)) < 1e-8 * np.max(np.abs(ref))
 
 
+def test_batch_chain_keeps_parameters_on_mniw_failure(golden, capsys):
+    """A Cholesky failure inside the MNIW update must not abort the chain: the reference catches the LinAlgError, prints
+    and keeps the previous posteriors of BOTH distributions for that member (GPI_model.py:1068-1071).  Forced here with a
+    non-SPD row covariance in the observation prior (every update fails, so the parameter sets that get appended are
+    the annealed prior's): states and parameters must follow the oracle, which mirrors the reference's except branch."""
+    import hdpgpc_b200 as hb
+    from hdpgpc_b200 import ops
+    z = golden("offline_rec100_T30_L1")
+    Y = z["data"][:, :, 0]
+    T = Y.shape[1]
+    pre = "chain_0_"
+    resp = np.zeros(Y.shape[0]); resp[:10] = 1.0
+    og = O.OracleGP(z["x_basis"], z["kernel_def"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]),
+                    free_deg=int(z["free_deg_MNIV"]))
+    og.observation.m_r_cov = -np.eye(T)
+    og.full_pass_weighted(Y, resp, fitted_kernel=z[pre + "kernel"])
+    gp = hb.GPI_model.fresh(z["x_basis"], z[pre + "kernel"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]),
+                            free_deg=float(z["free_deg_MNIV"]))
+    d = gp._chain_prepare(cu(Y), cu(resp))
+    d["obs_m_r_cov"].copy_(-torch.eye(T, dtype=torch.float64, device="cuda"))
+    ops.chain_run([d], T)
+    gp._chain_finish(d)
+    assert gp.mniw_first_failed_member == 1                  # the first update happens at the second member
+    assert "Alg error matrix ill conditioned." in capsys.readouterr().out
+    assert gp.A.shape[0] == len(og.A) == 11
+    for nm in ["A", "Gamma", "C", "Sigma", "cov_f", "cov_f_sm"]:
+        mine, ref = getattr(gp, nm).cpu().numpy(), np.stack(getattr(og, nm))
+        assert np.max(np.abs(mine - ref)) < 1e-8 * np.max(np.abs(ref)), nm
+    assert np.max(np.abs(gp.f_star_sm.cpu().numpy() - np.stack(og.f_star_sm).reshape(11, T))) < 1e-8 * np.max(np.abs(Y))
+    # the internal distribution was kept as well, although only the observation one is broken
+    assert torch.equal(gp.internal["m_mean"], torch.eye(T, dtype=torch.float64, device="cuda"))
+    assert float(gp.internal["n0"][0]) == float(z["free_deg_MNIV"])
+
+
 def test_chain_replay_with_device_hyperfit(golden):
     """The whole fresh-cluster path on the device: hyper-fit on the first member (a10), prior from the fitted kernel,
     chain replay (a5-a9), scores (a1, a4) -- against the reference run (whose hyper-fit is the autograd restatement)."""
@@ -835,6 +869,24 @@ def test_snr_tensor_core_path_vs_scalar_and_oracle(N, T, M):
     assert err(slow) < TOL and err(fast) < TOL
     if s_eq >= 0 and float(torch.sum(mu_sm[s_eq] ** 2)) > 0:
         assert float(fast[n_eq, 0]) > 100.0 and abs(float(fast[n_eq, 0]) - float(want[n_eq, 0])) < 1e-6
+
+
+@pytest.mark.parametrize("M", [40, 100])
+def test_snr_arbitrary_state_map(M):
+    """hgp_snr_states accepts ANY snr_state_of: with a random map nearly every beat of a 64-beat tile starts a new run of
+    every cluster (64 * M runs against the 128 / 192 rows of the tensor-core A operand) -- those tiles must take the
+    direct path and agree with the oracle; a second plane mixes overflowing tiles with regular ones."""
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(M)
+    N, T, S = 500, 90, 37
+    Y = cu(rng.normal(size=(N, T)) * 30.0)
+    mu = cu(rng.normal(size=(S, T)) * 30.0)
+    sso = rng.integers(-1, S, size=(N, M)).astype(np.int32)
+    sso[128:320] = sso[128][None, :]                                   # tiles 2..4: one run per cluster (regular path)
+    got = ops.snr_states(Y, mu, cu(sso).to(torch.int32))
+    want = cu(O.snr_states(Y.cpu().numpy(), mu.cpu().numpy(), np.maximum(sso, 0)))
+    want[cu(sso) < 0] = 0.0
+    assert float(torch.max(torch.abs(got - want) / torch.clamp(torch.abs(want), min=1.0))) < TOL
 
 
 @pytest.mark.parametrize("N,T", [(1000, 64), (300, 288)])

@@ -31,7 +31,7 @@ def _reference():
     return refshim, root
 
 
-def run_on_device(name, quiet=True):
+def run_on_device(name, quiet=True, profile=False):
     """(summary, wall seconds, kernel launches) of scenario `name` with the seam patched onto the device."""
     import hdpgpc_b200 as hb
     import hdpgpc_b200.integration as hgi
@@ -40,7 +40,8 @@ def run_on_device(name, quiet=True):
     hdp = refshim.install(root)
     import hdpgpc.GPI as gpi
     import hdpgpc.GPI_model as gm
-    hgi.enable(gm.GPI_model, hdp.GPI_HDP, gpi.IterativeGaussianProcess)
+    hgi.seam_times.clear()
+    hgi.enable(gm.GPI_model, hdp.GPI_HDP, gpi.IterativeGaussianProcess, profile=profile)
     launches0 = hb.ops.launch_count()
     try:
         with contextlib.redirect_stdout(io.StringIO() if quiet else sys.stdout):

@@ -20,7 +20,9 @@ def main():
     res = {}
     for name in names:
         t0 = time.time()
-        got, wall, launches, twins = run_on_device(name, quiet=not verbose)
+        got, wall, launches, twins = run_on_device(name, quiet=not verbose, profile=True)
+        import hdpgpc_b200.integration as hgi
+        stages = {k: [v[0], round(v[1], 3)] for k, v in sorted(hgi.seam_times.items(), key=lambda kv: -kv[1][1])}
         z = np.load(os.path.join(ROOT, "tests", "golden", f"fit_{name}.npz"))
         same = bool(np.array_equal(got["labels"], z["labels"])) and int(got["M"]) == int(z["M"])
         n_it = min(int(got["n_outer"]), int(z["n_outer"]))
@@ -37,7 +39,7 @@ def main():
                          elbo_rel_err=(np.abs(got["elbo"][:el] - z["elbo"][:el]) / np.abs(z["elbo"][:el])).tolist(),
                          kernels=got["kernels"].tolist(), kernels_ref=z["kernels"].tolist(),
                          device_s=round(wall, 2), cpu_reference_s=float(z["cpu_fit_seconds"]), gpu_launches=launches,
-                         total_s=round(time.time() - t0, 2))
+                         total_s=round(time.time() - t0, 2), seam_calls_seconds=stages)
         print(name, json.dumps(res[name]), flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"fit_{name}.json"), "w") as f:
