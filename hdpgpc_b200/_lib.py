@@ -44,6 +44,8 @@ PROTOTYPES = {
     "hgp_gemm_batched": (_int, [_p, _p, _p, _p, _p, _i64, _int, _int, _int, _p]),
     "hgp_chain_desc_bytes": (_i64, []),
     "hgp_chain_work_doubles": (_i64, [_int]),
+    "hgp_chain_rts_cache_doubles": (_i64, [_int, _int]),
+    "hgp_chain_small_path": (_int, [_int]),
     "hgp_chain_run": (_int, [_p, _int, _int, _p]),
     "hgp_la_op": (_int, [_int, _p, _p, _p, _p, _int, _p, _p]),
     "hgp_pred_dist_work_doubles": (_i64, [_i64, _int, _int]),
@@ -117,4 +119,5 @@ class ChainDesc(ctypes.Structure):
                 [(n, _p) for n in ("f_star", "f_star_sm", "cov_f", "cov_f_sm", "A", "Gamma", "C", "Sigma",
                                    "int_m_mean", "int_m_r_cov", "int_scale", "int_n0",
                                    "obs_m_mean", "obs_m_r_cov", "obs_scale", "obs_n0", "work", "piv", "status")] +
-                [("start_members", _int), ("start_params", _int), ("phases", _int), ("reserved_", _int)])
+                [("start_members", _int), ("start_params", _int), ("phases", _int), ("reserved_", _int),
+                 ("rts_cache", _p)])

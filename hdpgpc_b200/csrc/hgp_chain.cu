@@ -11,6 +11,7 @@
 // Shared basis grid only (x_train == x_basis: every shipped configuration); dynamic model (Gamma != 0).
 #include "hgp_common.cuh"
 #include "hgp_cta_la.cuh"
+#include "hgp_smem_la.cuh"
 
 using namespace hgp;
 
@@ -248,6 +249,300 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
     if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
 }
 
+// ======================================================================================================
+// Small systems (T <= 92: the MIT-BIH beat length is 90): the same chain on the shared-memory routines of
+// hgp_smem_la.cuh.  Beyond moving the operands into shared memory the step is re-organised around three facts
+// (each leaves the reference's arithmetic in place up to rounding):
+//   * every system solved in the chain is symmetric positive definite -- S = C P C^T + R (Kalman gain, GPI.py:145),
+//     P = A S0 A^T + Gamma (smoother gains, GPI.py:267, :297) -- so `solve` / `inv` become  chol -> L^{-1} -> two
+//     triangular tensor-core products (sl_cholinv) instead of a pivoted LU with latency-bound substitutions;
+//   * the pair smoother of member k (GPI_model.py:705-716) works on the covariance the Kalman update of the same
+//     member started from, with the same (A, Gamma): its P = A S0 A^T + Gamma and A S0 ARE the update's -- reused;
+//   * the full RTS pass (GPI.py:262-270) visits state i with the parameter set and the filtered covariance the pair
+//     smoother of the next member used: its gain J_i and its P_i are exactly the ones already computed on the way
+//     forward.  They are kept per member (`rts_cache`, 2 T^2 + T doubles per state), which turns a backward step
+//     from five products, an LU and a solve into two products.
+// One member costs 26 products (about half of them triangular) and 6 factorisations.
+
+// G0 = A S,  P = G0 A^T + Gamma
+__device__ __forceinline__ void small_predict(SlCtx& c, double* G0, double* P, const double* A, const double* Gm, const double* S) {
+    SlEpi e0;
+    sl_gemm(c, G0, A, 0, S, 0, e0);
+    SlEpi e1;
+    e1.beta = 1.0; e1.D = Gm;
+    sl_gemm(c, P, G0, 0, A, 1, e1);
+}
+// X = G^T M^{-1} for SPD M (M is symmetrised first):  Linv = chol(M)^{-1},  Z = Linv G,  X = Z^T Linv.
+// With G = C P this is the Kalman gain K = P C^T S^{-1}; with G = A S0 the smoother gain J = S0 A^T P^{-1}.
+__device__ __forceinline__ int small_gain(SlCtx& c, double* X, const double* Mspd, const double* G, double* Linv, double* Z) {
+    const int info = sl_cholinv(c, Linv, Mspd, 0.0);
+    SlEpi e;
+    sl_gemm(c, Z, Linv, 0, G, 0, e, SL_TRI_A);
+    sl_gemm(c, X, Z, 1, Linv, 0, e, SL_TRI_B);
+    return info;
+}
+
+__device__ __forceinline__ double small_mean_abs_diag(const double* A, int T, SlCtx& c) {
+    double p = 0.0;
+    for (int i = threadIdx.x; i < T; i += SL_THREADS) p += fabs(A[(int64_t)i * T + i]);
+    p = warp_sum(p);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) c.red[threadIdx.x >> 5] = p;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < SL_THREADS / 32; ++w) tot += c.red[w];
+    __syncthreads();
+    return tot / T;
+}
+
+// matrix_normal_inv_wishart.posterior, n_k = 1 (GPI_model.py:1300-1344): S2 -> Ga, part_mean -> Gb; d is only read.
+__device__ __noinline__ int small_mniw_compute(SlCtx& c, Mniw d, const double* y1, const double* y2, int T, double* Ga,
+                                               double* Gb, double* Gc, double* Gd, double* Ge) {
+    const int n = T * T;
+    const double jitter = 1e-2 * fmax(small_mean_abs_diag(d.scale, T, c), HGP_EPS);
+    int info = sl_cholinv(c, Gc, d.m_r_cov, jitter);                    // Ls^{-1}
+    if (info) return info;
+    SlEpi e;
+    sl_gemm(c, Ga, Gc, 1, Gc, 0, e, SL_TRI_A | SL_TRI_B);               // Sinv = Ls^{-T} Ls^{-1}
+    SlEpi e1;
+    e1.s = 1.0; e1.u = y1; e1.v = y2;
+    sl_gemm(c, Gd, d.m_mean, 0, Ga, 0, e1);                             // S1 = m_mean Sinv + y1 y2^T
+    sl_invalidate(c, Ga);
+    for (int i = threadIdx.x; i < n; i += SL_THREADS) Ga[i] += y2[i / T] * y2[i % T];      // S2 = Sinv + y2 y2^T
+    __syncthreads();
+    info = sl_cholinv(c, Gc, Ga, 1e-8);                                 // chol(sym(S2) + 1e-8 I)^{-1}
+    if (info) return info;
+    sl_gemm(c, Ge, Gd, 0, Gc, 1, e, SL_TRI_B);                          // S1 L2^{-T}
+    sl_gemm(c, Gb, Ge, 0, Gc, 0, e, SL_TRI_B);                          // part_mean = S1 S2^{-1}
+    return 0;
+}
+__device__ __noinline__ void small_mniw_commit(SlCtx& c, Mniw d, const double* y1, const double* y2, int T, const double* S2,
+                                               const double* part) {
+    const int n = T * T;
+    const double n0 = *d.n0;
+    const double a = (n0 - 2.0), den = (n0 + 1.0) - 2.0;
+    sl_invalidate(c, d.m_mean); sl_invalidate(c, d.scale); sl_invalidate(c, d.m_r_cov);
+    for (int i = threadIdx.x; i < n; i += SL_THREADS) {
+        const int r = i / T, cc = i % T;
+        d.m_mean[i] = (a * d.m_mean[i] + part[i]) / den;
+        const double e_r = y1[r] - y2[r], e_c = y1[cc] - y2[cc];
+        d.scale[i] = (a * d.scale[i] + e_r * e_c) / den;
+        d.m_r_cov[i] = S2[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *d.n0 = n0 + 1.0;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SL_THREADS, 1)
+chain_kernel_small(const hgp_chain_desc* __restrict__ descs, int T) {
+    __shared__ SlCtx c;
+    sl_init(c, T);
+    const hgp_chain_desc d = descs[blockIdx.x];
+    const int n = T * T;
+    const int64_t tt = (int64_t)T * T;
+    double* G[12];
+    for (int i = 0; i < 12; ++i) G[i] = d.work + i * tt;
+    double* v0 = d.work + 12 * tt; double* v1 = v0 + T; double* v2 = v1 + T;
+    Mniw mi{d.int_m_mean, d.int_m_r_cov, d.int_scale, d.int_n0};
+    Mniw mo{d.obs_m_mean, d.obs_m_r_cov, d.obs_scale, d.obs_n0};
+    const int n_tot = d.start_members + d.n_members;
+    double* Ph = d.rts_cache;                                            // [n_tot + 1][T][T]  P_s
+    double* Jh = Ph ? Ph + (int64_t)(n_tot + 1) * tt : nullptr;          //                    J_s
+    double* Vh = Ph ? Jh + (int64_t)(n_tot + 1) * tt : nullptr;          // [n_tot + 1][T]     A m_s
+    int fail = 0;
+    int N = d.start_members;
+    int p = d.start_params;
+    const int phases = d.phases ? d.phases : 15;
+    for (int k = 0; k < d.n_members; ++k) {
+        const int s = d.start_members + k;
+        const double* m = d.f_star_sm + (int64_t)s * T;
+        const double* Sg = d.cov_f_sm + s * tt;
+        const double* A = d.A + p * tt;
+        const double* Gm = d.Gamma + p * tt;
+        const double* C = d.C + p * tt;
+        const double* R = d.Sigma + p * tt;
+        const double* y = d.Y + (int64_t)d.member_beats[k] * T;
+        double* m_new = d.f_star + (int64_t)(s + 1) * T;
+        double* S_new = d.cov_f + (s + 1) * tt;
+        const bool prior = d.first_is_prior && s == 0;
+        double* Pc = Ph ? Ph + s * tt : G[1];
+        double* Am = Vh ? Vh + (int64_t)s * T : v0;
+        bool have_P = false;
+        // ---------------- Kalman update (GPI.py:104-150) ----------------
+        if (phases & 1) {
+            sl_gemv(Am, A, m, T, 0.0, nullptr);                          // A m
+            const double* P;
+            SlEpi e;
+            if (prior) {
+                P = Sg;                                                  // P_t = cov_prior; f* = 0; R = r_first I
+                for (int i = threadIdx.x; i < T; i += SL_THREADS) v1[i] = y[i];
+                __syncthreads();
+                sl_gemm(c, G[2], C, 0, P, 0, e);                         // C P
+                SlEpi es;
+                es.diag_add = d.r_first;
+                sl_gemm(c, G[3], G[2], 0, C, 1, es);                     // S = C P C^T + r I
+            } else {
+                small_predict(c, G[0], Pc, A, Gm, Sg);                   // G0 = A Sigma, P = A Sigma A^T + Gamma
+                have_P = true;
+                P = Pc;
+                sl_gemv(v2, C, Am, T, 0.0, nullptr);                     // f* = C A m
+                for (int i = threadIdx.x; i < T; i += SL_THREADS) v1[i] = y[i] - v2[i];
+                __syncthreads();
+                sl_gemm(c, G[2], C, 0, P, 0, e);                         // C P
+                SlEpi es;
+                es.beta = 1.0; es.D = R;
+                sl_gemm(c, G[3], G[2], 0, C, 1, es);                     // S = C P C^T + R
+            }
+            small_gain(c, G[6], G[3], G[2], G[4], G[5]);                 // K = P C^T S^{-1}
+            sl_gemv(m_new, G[6], v1, T, 1.0, Am);                        // m+ = A m + K (y - f*)
+            // Joseph form: (I - K C) P (I - K C)^T + K R K^T
+            SlEpi ei;
+            ei.alpha = -1.0; ei.diag_add = 1.0;
+            sl_gemm(c, G[7], G[6], 0, C, 0, ei);                         // I - K C
+            sl_gemm(c, G[8], G[7], 0, P, 0, e);                          // (I - K C) P
+            sl_gemm(c, G[9], G[8], 0, G[7], 1, e);                       // ... (I - K C)^T
+            SlEpi ej;
+            ej.beta = 1.0; ej.D = G[9];
+            if (prior) {
+                ej.alpha = d.r_first;
+                sl_gemm(c, S_new, G[6], 0, G[6], 1, ej, 0, d.cov_f_sm + (s + 1) * tt);      // + r K K^T
+            } else {
+                sl_gemm(c, G[5], G[6], 0, R, 0, e);                      // K R
+                sl_gemm(c, S_new, G[5], 0, G[6], 1, ej, 0, d.cov_f_sm + (s + 1) * tt);      // + K R K^T
+            }
+            sl_copy(d.f_star_sm + (int64_t)(s + 1) * T, m_new, T);
+        }
+        N += 1;
+        // ---------------- pair smoother (GPI_model.py:705-716, GPI.py:294-299) ----------------
+        if ((phases & 2) && N > 1) {
+            const double* m0 = d.f_star + (int64_t)s * T;
+            const double* S0 = d.cov_f + s * tt;
+            if (!have_P) {                                               // phase called on its own (online seam)
+                sl_gemv(Am, A, m0, T, 0.0, nullptr);
+                small_predict(c, G[0], Pc, A, Gm, S0);
+            }
+            double* Jc = Jh ? Jh + s * tt : G[6];
+            small_gain(c, Jc, Pc, G[0], G[4], G[5]);                     // J = S0 A^T P^{-1}
+            for (int i = threadIdx.x; i < T; i += SL_THREADS) v2[i] = m_new[i] - Am[i];
+            __syncthreads();
+            sl_gemv(d.f_star_sm + (int64_t)s * T, Jc, v2, T, 1.0, m0);   // m0 + J (m1 - A m0)
+            sl_invalidate(c, G[7]);
+            sl_axpby(G[7], 1.0, S_new, -1.0, Pc, n);                     // S1 - P
+            SlEpi e;
+            sl_gemm(c, G[8], Jc, 0, G[7], 0, e);                         // J (S1 - P)
+            SlEpi es;
+            es.beta = 1.0; es.D = S0;
+            sl_gemm(c, d.cov_f_sm + s * tt, G[8], 0, Jc, 1, es);         // S0 + J (S1 - P) J^T
+        }
+        // ---------------- MNIW step (GPI_model.py:966-1101) ----------------
+        if (!(phases & 4)) continue;
+        const bool below = d.estimation_limit <= 0 || N < d.estimation_limit;
+        if (N > 1 && below) {
+            const double* f1 = d.f_star_sm + (int64_t)(s + 1) * T;
+            const double* f0 = d.f_star_sm + (int64_t)s * T;
+            const int i1 = small_mniw_compute(c, mi, f1, f0, T, G[0], G[2], G[3], G[4], G[5]);
+            const int i2 = i1 ? 0 : small_mniw_compute(c, mo, y, f1, T, G[6], G[7], G[8], G[9], G[10]);
+            if (i1 || i2) {
+                if (!fail) fail = k + 1;
+            } else {
+                small_mniw_commit(c, mi, f1, f0, T, G[0], G[2]);
+                small_mniw_commit(c, mo, y, f1, T, G[6], G[7]);
+            }
+        }
+        if (below) {
+            double* An = d.A + (p + 1) * tt; double* Gn = d.Gamma + (p + 1) * tt;
+            double* Cn = d.C + (p + 1) * tt; double* Sn = d.Sigma + (p + 1) * tt;
+            const double gi = *d.int_n0, go = *d.obs_n0;
+            const double fa = d.annealing ? 1.0 / ((double)N * (double)N) : 0.0;
+            for (int i = threadIdx.x; i < n; i += SL_THREADS) {
+                An[i] = d.int_m_mean[i];
+                Cn[i] = d.obs_m_mean[i];
+                const double g = (N > 1) ? d.int_scale[i] * gi / (gi - 2.0) : Gm[i];
+                const double sg = (N > 1) ? d.obs_scale[i] * go / (go - 2.0) : R[i];
+                Gn[i] = g + fa * d.Gamma[i];          // + Gamma[0] / N^2
+                Sn[i] = sg + fa * d.Sigma[i];         // + Sigma[0] / N^2
+            }
+            __syncthreads();
+            p += 1;
+        }
+    }
+    // ---------------- full RTS pass (GPI_model.py:687-703, GPI.py:262-270) ----------------
+    const int Tn = n_tot;
+    const int nA = p;
+    if (!(phases & 8)) {
+        if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
+        return;
+    }
+    if (Tn >= 1) {
+        sl_copy(d.f_star_sm + (int64_t)Tn * T, d.f_star + (int64_t)Tn * T, T);
+        sl_invalidate(c, d.cov_f_sm + Tn * tt);
+        sl_copy(d.cov_f_sm + Tn * tt, d.cov_f + Tn * tt, n);
+    }
+    const bool cached = Ph != nullptr && d.start_members == 0 && (phases & 3) == 3;
+    for (int t = Tn - 2; t >= 0; --t) {
+        const int i = t + 1;                                            // state index
+        const int ia = (t < nA ? t : nA - 1) + 1;
+        const double* A = d.A + ia * tt;
+        const double* Gm = d.Gamma + ia * tt;
+        const double* mt = d.f_star + (int64_t)i * T;
+        const double* St = d.cov_f + i * tt;
+        const double* mn = d.f_star_sm + (int64_t)(i + 1) * T;
+        const double* Sn = d.cov_f_sm + (i + 1) * tt;
+        const double *Pt, *Jt, *Amt;
+        if (cached) {                                                   // the forward pass left P_i, J_i and A m_i behind
+            Pt = Ph + i * tt; Jt = Jh + i * tt; Amt = Vh + (int64_t)i * T;
+        } else {
+            sl_gemv(v0, A, mt, T, 0.0, nullptr);
+            small_predict(c, G[0], G[1], A, Gm, St);
+            small_gain(c, G[6], G[1], G[0], G[4], G[5]);
+            Pt = G[1]; Jt = G[6]; Amt = v0;
+        }
+        for (int j = threadIdx.x; j < T; j += SL_THREADS) v2[j] = mn[j] - Amt[j];
+        __syncthreads();
+        sl_gemv(d.f_star_sm + (int64_t)i * T, Jt, v2, T, 1.0, mt);
+        sl_invalidate(c, G[7]);
+        sl_axpby(G[7], 1.0, Sn, -1.0, Pt, n);
+        SlEpi e;
+        sl_gemm(c, G[8], Jt, 0, G[7], 0, e);
+        SlEpi es;
+        es.beta = 1.0; es.D = St;
+        sl_gemm(c, d.cov_f_sm + i * tt, G[8], 0, Jt, 1, es);
+    }
+    if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
+}
+
+// unit-test hook for the shared-memory routines
+__global__ void __launch_bounds__(SL_THREADS, 1)
+sl_op_kernel(int op, double* A, double* B, double* Cm, int T, int* info) {
+    __shared__ SlCtx c;
+    sl_init(c, T);
+    int rc = 0;
+    SlEpi e;
+    switch (op) {
+        case 10: sl_gemm(c, Cm, A, 0, B, 0, e); break;
+        case 11: sl_gemm(c, Cm, A, 1, B, 0, e); break;
+        case 12: sl_gemm(c, Cm, A, 0, B, 1, e); break;
+        case 13: { SlEpi f; f.alpha = 2.0; f.beta = -1.0; f.D = Cm; f.diag_add = 0.5; sl_gemm(c, Cm, A, 1, B, 1, f); } break;
+        case 14: rc = sl_cholinv(c, Cm, A, 0.25); if (threadIdx.x == 0) B[0] = c.logdet; break;   // Cm = chol(sym A + .25 I)^-1
+        case 15: {   // Cm = A^T M^{-1} via small_gain (M = B SPD); scratch: the two T x T blocks behind Cm
+            rc = small_gain(c, Cm, B, A, Cm + (int64_t)T * T, Cm + 2 * (int64_t)T * T);
+        } break;
+        case 16: sl_gemm(c, Cm, A, 0, B, 0, e, SL_TRI_A); break;      // A lower triangular
+        case 17: sl_gemm(c, Cm, A, 1, B, 0, e, SL_TRI_A | SL_TRI_B); break;   // A^T B, both lower triangular
+        case 18: sl_gemm(c, Cm, A, 0, B, 1, e, SL_TRI_B); break;      // A B^T, B lower triangular
+        // steady-state cost of the routines inside one launch (tools/la_bench.py divides by 64)
+        case 20: for (int i = 0; i < 64; ++i) sl_gemm(c, Cm, A, 0, B, 0, e); break;                 // operands stay cached
+        case 21: for (int i = 0; i < 32; ++i) { sl_gemm(c, Cm, A, 0, B, 0, e); sl_gemm(c, Cm + (int64_t)T * T, B, 1, Cm, 0, e);
+                                                 sl_invalidate(c, A); } break;                      // one operand miss per product
+        case 22: for (int i = 0; i < 64; ++i) rc |= sl_cholinv(c, Cm, A, 0.25); break;
+        case 23: for (int i = 0; i < 64; ++i) sl_gemv(Cm, A, B, T, 0.0, nullptr); break;
+        case 24: for (int i = 0; i < 64; ++i) { sl_invalidate(c, Cm); sl_axpby(Cm, 1.0, A, -1.0, B, T * T); } break;
+        default: rc = -1;
+    }
+    if (threadIdx.x == 0) info[0] = rc;
+}
+
 // unit-test hook for the CTA-level routines: op codes below
 __global__ void __launch_bounds__(LA_THREADS)
 la_op_kernel(int op, double* A, double* B, double* C, int* piv, int T, int* info) {
@@ -275,11 +570,24 @@ la_op_kernel(int op, double* A, double* B, double* C, int* piv, int T, int* info
 }  // namespace
 
 extern "C" int64_t hgp_chain_desc_bytes(void) { return (int64_t)sizeof(hgp_chain_desc); }
-extern "C" int64_t hgp_chain_work_doubles(int T) { return 8 * (int64_t)T * T + 8 * (int64_t)T; }
+extern "C" int64_t hgp_chain_work_doubles(int T) { return 12 * (int64_t)T * T + 8 * (int64_t)T; }
+extern "C" int64_t hgp_chain_rts_cache_doubles(int T, int n_states) {
+    return sl_supported(T) ? (int64_t)n_states * (2 * (int64_t)T * T + T) : 0;
+}
+extern "C" int hgp_chain_small_path(int T) { return sl_supported(T) && !getenv("HGP_CHAIN_V1") ? 1 : 0; }
 
 extern "C" int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream) {
     HGP_REQUIRE(n_chains >= 0 && T > 0 && T <= 1024, "hgp_chain_run: bad sizes");
     if (n_chains == 0) return 0;
+    if (hgp_chain_small_path(T)) {
+        const size_t sdyn = sl_dynamic_smem_bytes(T);
+        cudaError_t e = cudaFuncSetAttribute(chain_kernel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdyn);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_chain_run: shared memory (small path)");
+        chain_kernel_small<<<n_chains, SL_THREADS, sdyn, (cudaStream_t)stream>>>(
+            reinterpret_cast<const hgp_chain_desc*>(descs_device), T);
+        HGP_LAUNCH_CHECK("hgp_chain_run");
+        return 0;
+    }
     const size_t dyn = la_dynamic_smem_bytes(T);
     if (dyn > 0) {
         cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -292,6 +600,15 @@ extern "C" int hgp_chain_run(const void* descs_device, int n_chains, int T, void
 
 extern "C" int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream) {
     HGP_REQUIRE(T > 0 && T <= 1024, "hgp_la_op: bad T");
+    if (op >= 10) {      // shared-memory routines (hgp_smem_la.cuh)
+        HGP_REQUIRE(sl_supported(T), "hgp_la_op: T outside the shared-memory path");
+        const size_t sdyn = sl_dynamic_smem_bytes(T);
+        cudaError_t e = cudaFuncSetAttribute(sl_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdyn);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_la_op: shared memory");
+        sl_op_kernel<<<1, SL_THREADS, sdyn, (cudaStream_t)stream>>>(op, A, B, C, T, info);
+        HGP_LAUNCH_CHECK("hgp_la_op");
+        return 0;
+    }
     const size_t dyn = la_dynamic_smem_bytes(T);
     if (dyn > 0) {
         cudaError_t e = cudaFuncSetAttribute(la_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

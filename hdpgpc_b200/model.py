@@ -761,7 +761,8 @@ class GPI_model:
                     obs_m_mean=self.C[0].clone(), obs_m_r_cov=eye.clone(), obs_scale=self.Sigma[0].clone(),
                     obs_n0=torch.tensor([self.free_deg], dtype=F64, device=dev),
                     work=z(int(lib.hgp_chain_work_doubles(T))), piv=torch.zeros(T, dtype=torch.int32, device=dev),
-                    status=torch.zeros(2, dtype=torch.int32, device=dev))
+                    status=torch.zeros(2, dtype=torch.int32, device=dev),
+                    rts_cache=torch.empty(max(1, int(lib.hgp_chain_rts_cache_doubles(T, n + 1))), dtype=F64, device=dev))
 
     def _chain_finish(self, desc):
         fail, n_par = (int(v) for v in desc["status"])

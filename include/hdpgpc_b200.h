@@ -216,9 +216,16 @@ typedef struct hgp_chain_desc {
     int start_params;         /* index of the last parameter set (A, Gamma, C, Sigma) already written (0: fresh chain) */
     int phases;               /* bit 0 Kalman update, bit 1 pair smoother, bit 2 MNIW step, bit 3 full RTS pass; 0 = all */
     int reserved_;
+    /* Optional (may be NULL), >= hgp_chain_rts_cache_doubles(T, start_members + n_members + 1) doubles: the shared-memory
+     * path for small T (hgp_chain_small_path) keeps the smoother gain J_s, the predicted covariance P_s and A m_s of every
+     * state it passes on the way forward, so that the full RTS pass re-uses them instead of re-deriving them (the pass
+     * visits state s with exactly the parameters and the filtered covariance the pair smoother used). */
+    double* rts_cache;
 } hgp_chain_desc;
 int64_t hgp_chain_desc_bytes(void);
 int64_t hgp_chain_work_doubles(int T);
+int64_t hgp_chain_rts_cache_doubles(int T, int n_states);   /* 0 when T is outside the shared-memory path */
+int hgp_chain_small_path(int T);                            /* 1: hgp_chain_run uses the shared-memory kernel for this T */
 int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream);
 /* Unit-test hook for the CTA-level routines the chain kernel is built from (gemm variants, chol, trsm, LU solve). */
 int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream);

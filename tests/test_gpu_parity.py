@@ -177,6 +177,47 @@ def test_cta_linear_algebra(T):
     assert ops.la_op(4, bad) == T
 
 
+@pytest.mark.parametrize("T", [12, 30, 45, 64, 90, 92])
+def test_shared_memory_linear_algebra(T):
+    """The shared-memory routines of the small-T chain kernel (hgp_smem_la.cuh) against numpy: products with every
+    transposition / triangular hint / epilogue term through the three-buffer operand cache, the blocked Cholesky that
+    returns the inverse factor (and the log-determinant), the SPD solve built from it, and the non-SPD report."""
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(T)
+    A = rng.standard_normal((T, T)); B = rng.standard_normal((T, T)); C0 = rng.standard_normal((T, T))
+    close = lambda got, ref, tol=1e-12: np.max(np.abs(got.cpu().numpy() - ref)) < tol * np.max(np.abs(ref))
+    for op, ref in ((10, A @ B), (11, A.T @ B), (12, A @ B.T)):
+        C = cu(np.zeros((T, T)))
+        assert ops.la_op(op, cu(A), cu(B), C) == 0
+        assert close(C, ref)
+    C = cu(C0)
+    ops.la_op(13, cu(A), cu(B), C)
+    assert close(C, 2.0 * A.T @ B.T - C0 + 0.5 * np.eye(T))
+    Lo, Lb = np.tril(A), np.tril(B)
+    for op, a, b, ref in ((16, Lo, B, Lo @ B), (17, Lo, Lb, Lo.T @ Lb), (18, A, Lb, A @ Lb.T)):
+        C = cu(np.zeros((T, T)))
+        assert ops.la_op(op, cu(a), cu(b), C) == 0
+        assert close(C, ref)
+    S = random_spd(rng, 1, T, cond=1e6)[0]
+    S_ns = S + 1e-9 * rng.standard_normal((T, T))                    # the routine symmetrises its input
+    Li = cu(np.zeros((T, T))); aux = cu(np.zeros((T, T)))
+    assert ops.la_op(14, cu(S_ns), aux, Li) == 0
+    Sj = 0.5 * (S_ns + S_ns.T) + 0.25 * np.eye(T)
+    Lr = np.linalg.cholesky(Sj)
+    got = Li.cpu().numpy()
+    assert np.max(np.abs(np.triu(got, 1))) == 0.0
+    assert np.max(np.abs(got @ Lr - np.eye(T))) < 1e-10
+    assert abs(float(aux[0, 0]) - np.linalg.slogdet(Sj)[1]) < 1e-10 * abs(np.linalg.slogdet(Sj)[1])
+    X = cu(np.zeros((3, T, T)))
+    assert ops.la_op(15, cu(A), cu(S), X, T=T) == 0                  # X[0] = A^T S^{-1}
+    ref = A.T @ np.linalg.inv(S)
+    assert np.max(np.abs(X[0].cpu().numpy() - ref)) < 1e-9 * np.max(np.abs(ref))
+    bad = np.eye(T); bad[T - 1, T - 1] = -1.0
+    assert ops.la_op(14, cu(bad), aux, Li) == T
+    bad = np.eye(T); bad[0, 0] = -1.0
+    assert ops.la_op(14, cu(bad), aux, Li) == 1
+
+
 @pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2", "offline_rec100_T90_L1"])
 def test_chain_replay_vs_reference(golden, name):
     """full_pass_weighted on the device (Kalman + pair smoother + MNIW per member, full RTS pass) against the
