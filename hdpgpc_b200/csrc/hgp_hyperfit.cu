@@ -10,6 +10,7 @@
 // the CTA-level Cholesky / triangular solves of hgp_cta_la.cuh; nothing returns to the host in between.
 #include "hgp_common.cuh"
 #include "hgp_cta_la.cuh"
+#include "hgp_smem_la.cuh"
 
 using namespace hgp;
 
@@ -132,6 +133,124 @@ hyperfit_kernel(const double* __restrict__ x, const double* __restrict__ Y, int 
     }
 }
 
+// Small systems (T <= 92, the MIT-BIH beat length): the whole iteration lives in shared memory (hgp_smem_la.cuh).
+// Buffer 0 holds E = exp(-0.5 d^2 / l^2), buffer 1 holds K (destroyed by the factorisation, then K^-1 = L^-T L^-1 as a
+// triangular tensor-core product), buffer 2 the inverse factor; nothing but x and y is read from global memory.
+__device__ __forceinline__ double block_sum_sl(double v, SlCtx& c) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) c.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < SL_THREADS / 32; ++w) tot += c.red[w];
+    return tot;
+}
+
+__global__ void __launch_bounds__(SL_THREADS, 1)
+hyperfit_kernel_small(const double* __restrict__ x, const double* __restrict__ Y, int T, double lo, double hi, double lr,
+                      int max_iter, int min_iter, double atol, double* __restrict__ out) {
+    __shared__ SlCtx c;
+    __shared__ double s_raw[4], s_m[4], s_v[4], s_hist[11];
+    __shared__ double s_x[96], s_r[96], s_al[96];
+    __shared__ int s_stop, s_count;
+    sl_init(c, T);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int LD = c.LD;
+    const int64_t fit = blockIdx.x;
+    const double* y = Y + fit * T;
+    double* E = sl_dyn;
+    double* K = sl_dyn + c.stride;
+    if (tid < 4) { s_raw[tid] = 0.0; s_m[tid] = 0.0; s_v[tid] = 0.0; }
+    if (tid == 0) { s_stop = 0; s_count = 0; }
+    for (int i = tid; i < T; i += SL_THREADS) s_x[i] = x[i];
+    __syncthreads();
+    double b1p = 1.0, b2p = 1.0;
+    int info_any = 0;
+    int it = 0;
+    for (; it < max_iter; ++it) {
+        const double cm = s_raw[0];
+        const double sc = softplus_d(s_raw[1]);
+        const double ell = softplus_d(s_raw[2]);
+        const double sg_n = sigmoid_d(s_raw[3]);
+        const double noise = lo + (hi - lo) * sg_n;
+        const double ell2 = ell * ell;
+        for (int idx = tid; idx < T * T; idx += SL_THREADS) {
+            const int i = idx / T, j = idx - i * T;
+            const double d = s_x[i] - s_x[j];
+            const double e = exp(-0.5 * (d * d) / ell2);
+            E[i * LD + j] = e;
+            K[i * LD + j] = sc * e + (i == j ? noise : 0.0);
+        }
+        for (int i = tid; i < T; i += SL_THREADS) s_r[i] = y[i] - cm;
+        __syncthreads();
+        info_any |= sl_cholinv_buf(c, 1, 2, 0.0);               // buffer 2 = L^-1, c.logdet = 2 sum log L_ii
+        const double logd = 0.5 * c.logdet;
+        sl_gemm_buf(c, 1, 2, 1, 2, 0, SL_TRI_A | SL_TRI_B);     // buffer 1 = K^-1 = L^-T L^-1
+        // alpha = K^-1 r: one warp per row
+        for (int r = warp; r < T; r += SL_THREADS / 32) {
+            double a = 0.0;
+            for (int k = lane; k < T; k += 32) a += K[r * LD + k] * s_r[k];
+            a = warp_sum(a);
+            if (lane == 0) s_al[r] = a;
+        }
+        __syncthreads();
+        double p_quad = 0.0, p_sa = 0.0, p_gn = 0.0;
+        for (int i = tid; i < T; i += SL_THREADS) {
+            p_quad += s_r[i] * s_al[i];
+            p_sa += s_al[i];
+            p_gn += s_al[i] * s_al[i] - K[i * LD + i];
+        }
+        double p_gs = 0.0, p_gl = 0.0;
+        for (int idx = tid; idx < T * T; idx += SL_THREADS) {
+            const int i = idx / T, j = idx - i * T;
+            const double d = s_x[i] - s_x[j];
+            const double w = (s_al[i] * s_al[j] - K[i * LD + j]) * E[i * LD + j];
+            p_gs += w;
+            p_gl += w * (d * d);
+        }
+        const double quad = block_sum_sl(p_quad, c), sa = block_sum_sl(p_sa, c);
+        const double gn = block_sum_sl(p_gn, c), gs = block_sum_sl(p_gs, c), gl = block_sum_sl(p_gl, c);
+        b1p *= 0.9;
+        b2p *= 0.999;
+        if (tid == 0) {
+            const double loss = (0.5 * quad + logd + 0.5 * (double)T * HGP_LOG2PI) / (double)T;
+            const double k = -0.5 / (double)T;
+            double g[4];
+            g[0] = -sa / (double)T;
+            g[1] = k * gs * sigmoid_d(s_raw[1]);
+            g[2] = k * (sc * gl / (ell2 * ell)) * sigmoid_d(s_raw[2]);
+            g[3] = k * gn * (hi - lo) * sg_n * (1.0 - sg_n);
+            const double bc1 = 1.0 - b1p, bc2 = 1.0 - b2p;
+            for (int p = 0; p < 4; ++p) {
+                s_m[p] = 0.9 * s_m[p] + (1.0 - 0.9) * g[p];
+                s_v[p] = 0.999 * s_v[p] + (1.0 - 0.999) * g[p] * g[p];
+                s_raw[p] -= (lr / bc1) * s_m[p] / (sqrt(s_v[p]) / sqrt(bc2) + 1e-8);
+            }
+            for (int h = 0; h < 10; ++h) s_hist[h] = s_hist[h + 1];
+            s_hist[10] = loss;
+            s_count += 1;
+            if (s_count > min_iter) {
+                double dsum = 0.0;
+                for (int h = 0; h < 10; ++h) dsum += s_hist[h + 1] - s_hist[h];
+                if (fabs(dsum) <= atol) s_stop = 1;
+            }
+        }
+        __syncthreads();
+        if (s_stop) { ++it; break; }
+    }
+    if (tid == 0) {
+        double* o = out + fit * 8;
+        o[0] = softplus_d(s_raw[1]);
+        o[1] = softplus_d(s_raw[2]);
+        o[2] = lo + (hi - lo) * sigmoid_d(s_raw[3]);
+        o[3] = s_raw[0];
+        o[4] = s_hist[10];
+        o[5] = (double)it;
+        o[6] = (double)info_any;
+        o[7] = 0.0;
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t hgp_hyperfit_work_doubles(int n_fits, int T) { return (int64_t)n_fits * (3 * (int64_t)T * T + 2 * T); }
@@ -142,6 +261,15 @@ extern "C" int hgp_hyperfit_batched(const double* x, const double* Y, int n_fits
     HGP_REQUIRE(n_fits >= 0 && T > 0 && T <= 1024 && max_iter >= 0 && noise_hi >= noise_lo,
                 "hgp_hyperfit_batched: bad arguments");
     if (n_fits == 0) return 0;
+    if (sl_supported(T) && !getenv("HGP_HYPERFIT_V1")) {
+        const size_t sdyn = sl_dynamic_smem_bytes(T);
+        cudaError_t e = cudaFuncSetAttribute(hyperfit_kernel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdyn);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_hyperfit_batched: shared memory");
+        hyperfit_kernel_small<<<(unsigned)n_fits, SL_THREADS, sdyn, (cudaStream_t)stream>>>(x, Y, T, noise_lo, noise_hi, lr,
+                                                                                            max_iter, min_iter, atol, out);
+        HGP_LAUNCH_CHECK("hgp_hyperfit_batched");
+        return 0;
+    }
     hyperfit_kernel<<<(unsigned)n_fits, LA_THREADS, 0, (cudaStream_t)stream>>>(x, Y, T, noise_lo, noise_hi, lr, max_iter,
                                                                              min_iter, atol, out, work);
     HGP_LAUNCH_CHECK("hgp_hyperfit_batched");

@@ -340,9 +340,8 @@ static __device__ __noinline__ void sl_gemm(SlCtx& c, double* Cg, const double* 
 // Linv (global, dense, lower triangular, upper part zero) = chol(0.5 (M + M^T) + add_diag I)^{-1}; M global dense SPD.
 // Returns 0 or (index + 1) of the first non-positive pivot (Linv is then garbage).  c.logdet = log det of the
 // factorised matrix (2 sum log L_jj).
-static __device__ __noinline__ int sl_cholinv(SlCtx& c, double* Linv_g, const double* Mg, double add_diag) {
-    const int ix = sl_get(c, Mg);
-    const int iy = sl_alloc(c, ix, -1);
+// Buffer form: X = buffer ix (destroyed), Y = buffer iy receives the inverse factor; tags are the caller's business.
+static __device__ __noinline__ int sl_cholinv_buf(SlCtx& c, int ix, int iy, double add_diag) {
     const int T = c.T, LD = c.LD, TP = c.TP;
     double* X = sl_dyn + ix * c.stride;
     double* Y = sl_dyn + iy * c.stride;
@@ -357,7 +356,7 @@ static __device__ __noinline__ int sl_cholinv(SlCtx& c, double* Linv_g, const do
         } else if (cc == r) X[r * LD + r] += add_diag;
         Y[r * LD + cc] = 0.0;
     }
-    if (tid == 0) { c.flag = 0; c.logdet = 0.0; c.tag[ix] = nullptr; }     // X is destroyed below
+    if (tid == 0) { c.flag = 0; c.logdet = 0.0; }
     __syncthreads();
     for (int k0 = 0; k0 < T; k0 += SL_NB) {
         const int nb = min(SL_NB, T - k0), k1 = k0 + nb;
@@ -522,9 +521,19 @@ static __device__ __noinline__ int sl_cholinv(SlCtx& c, double* Linv_g, const do
         }
         __syncthreads();
     }
-    const int info = c.flag;
+    return c.flag;
+}
+
+static __device__ __noinline__ int sl_cholinv(SlCtx& c, double* Linv_g, const double* Mg, double add_diag) {
+    const int ix = sl_get(c, Mg);
+    const int iy = sl_alloc(c, ix, -1);
+    if (threadIdx.x == 0) c.tag[ix] = nullptr;               // X is destroyed by the factorisation
+    __syncthreads();
+    const int info = sl_cholinv_buf(c, ix, iy, add_diag);
     // write through
     {
+        const int T = c.T, LD = c.LD, tid = threadIdx.x;
+        const double* Y = sl_dyn + iy * c.stride;
         constexpr int U = 4;
         const int n = T * T;
         for (int i0 = tid; i0 < n; i0 += SL_THREADS * U) {
@@ -534,13 +543,59 @@ static __device__ __noinline__ int sl_cholinv(SlCtx& c, double* Linv_g, const do
                 if (i < n) { const int r = i / T, cc = i - r * T; Linv_g[i] = Y[r * LD + cc]; }
             }
         }
-    }
-    if (tid == 0) {
-        for (int i = 0; i < 3; ++i) if (c.tag[i] == Linv_g) c.tag[i] = nullptr;
-        sl_touch(c, iy, Linv_g);
+        if (tid == 0) {
+            for (int i = 0; i < 3; ++i) if (c.tag[i] == Linv_g) c.tag[i] = nullptr;
+            sl_touch(c, iy, Linv_g);
+        }
     }
     __syncthreads();
     return info;
+}
+
+// Buffer form of the product: buffer ic = op(buffer ia) op(buffer ib) (ic must differ from ia and ib); nothing goes to
+// global memory, tags are the caller's business.  Used where a whole iteration lives in shared memory (hyper-fit).
+static __device__ __noinline__ void sl_gemm_buf(SlCtx& c, int ic, int ia, int tA, int ib, int tB, int tri = 0) {
+    __syncthreads();
+    const int T = c.T, LD = c.LD, TP = c.TP, stride = c.stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int ntile = TP >> 3;
+    const int mtw = (ntile + 3) >> 2, ntw = (ntile + 1) >> 1;
+    const int mt0 = wm * mtw, nt0 = wn * ntw;
+    const int mcnt = max(0, min(mtw, ntile - mt0)), ncnt = max(0, min(ntw, ntile - nt0));
+    double acc[SL_MT][SL_NT][2];
+#pragma unroll
+    for (int i = 0; i < SL_MT; ++i)
+#pragma unroll
+        for (int j = 0; j < SL_NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    if (mcnt > 0 && ncnt > 0) {
+        const int r0 = mt0 * 8, r1 = (mt0 + mcnt) * 8, c0 = nt0 * 8, c1 = (nt0 + ncnt) * 8;
+        int klo = 0, khi = c.K4;
+        if (tri & SL_TRI_A) { if (tA) klo = max(klo, r0); else khi = min(khi, r1); }
+        if (tri & SL_TRI_B) { if (tB) khi = min(khi, c1); else klo = max(klo, c0); }
+        klo &= ~3;
+        khi = min(c.K4, (khi + 3) & ~3);
+        if (!tA && !tB) sl_mma_core<0, 0, false>(acc, ia, ib, stride, LD, r0, c0, mcnt, ncnt, klo, khi, lane);
+        else if (tA && !tB) sl_mma_core<1, 0, false>(acc, ia, ib, stride, LD, r0, c0, mcnt, ncnt, klo, khi, lane);
+        else if (!tA && tB) sl_mma_core<0, 1, false>(acc, ia, ib, stride, LD, r0, c0, mcnt, ncnt, klo, khi, lane);
+        else sl_mma_core<1, 1, false>(acc, ia, ib, stride, LD, r0, c0, mcnt, ncnt, klo, khi, lane);
+        const int lr = lane >> 2, lk = lane & 3;
+        double* Cs = sl_dyn + ic * stride;
+#pragma unroll
+        for (int i = 0; i < SL_MT; ++i) {
+            if (i >= mcnt) continue;
+            const int r = r0 + 8 * i + lr;
+            if (r >= T) continue;
+#pragma unroll
+            for (int j = 0; j < SL_NT; ++j) {
+                if (j >= ncnt) continue;
+                const int cc = c0 + 8 * j + 2 * lk;
+                if (cc < T) Cs[r * LD + cc] = acc[i][j][0];
+                if (cc + 1 < T) Cs[r * LD + cc + 1] = acc[i][j][1];
+            }
+        }
+    }
+    __syncthreads();
 }
 
 }  // namespace hgp
