@@ -52,7 +52,7 @@ def f_beat(T, L, M):
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference loop, timed on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_sweep_beats_per_s(n_beats, T, L, M, steps=1, seed=1234):
+def cpu_sweep_beats_per_s(n_beats, T, L, M, steps=1, seed=1234, outputs=None):
     import numpy as np
     import torch
     from hdpgpc_b200 import synthetic
@@ -71,9 +71,118 @@ def cpu_sweep_beats_per_s(n_beats, T, L, M, steps=1, seed=1234):
             fos = tb["factor_of_state"]
             q[:, :, ld] = O.score_states(Ys[ld], tb["mu"], tb["Sigma"], tb["state_of"], fos, tb["add_diag"][fos])
             snr[:, :, ld] = O.snr_states(Ys[ld], tb["mu_sm"], tb["snr_state_of"])
-        O.estep_responsibilities(q, snr, wl["transTheta"], wl["startTheta"])
+        r = O.estep_responsibilities(q, snr, wl["transTheta"], wl["startTheta"])
         times.append(time.perf_counter() - t0)
+    if outputs is not None:
+        outputs.update(q=q, snr=snr, z=r["z"], transStateCount=r["transStateCount"])
     return n_beats / (sum(times) / len(times)), cores, times
+
+
+def reference_sweep_beats_per_s(n_beats, T, L, M, steps=1, seed=1234, outputs=None):
+    """The same sweep by the UNMODIFIED reference (torch CPU), imported through oracle/refshim from /root/reference or from
+    the copy tools/make_ref.sh stages under oracle/_ref: per (cluster, lead) `GPI_model.compute_sq_err_all`
+    (GPI_model.py:488-547) and `GPI_HDP.compute_snr` (GPI_HDP.py:732-748) on reference model objects that hold the
+    workload's cluster states, then the HMM block of `estimate_q_all` (GPI_HDP.py:2856-2862: weight_mean, LogLik, forward,
+    backward, coupled_state_coef, _safe_exp) and the count lines (:890-892).  Returns None if the reference is not there."""
+    import contextlib
+    import io
+    import numpy as np
+    import torch
+    from scipy.special import digamma
+    from hdpgpc_b200 import synthetic
+    from oracle import refshim                 # bench.py's cpu_baseline / reference arm may execute oracle/
+    if refshim.find_reference() is None:
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    with contextlib.redirect_stdout(io.StringIO()):
+        hdp = refshim.install()
+    wl = synthetic.make_workload(n_beats, T=T, L=L, M=M, seed=seed, device="cpu")
+    labels = wl["labels"]
+    x_basis = np.atleast_2d(np.arange(T, dtype=np.float64)).T
+    with contextlib.redirect_stdout(io.StringIO()):
+        sw = hdp.GPI_HDP(x_basis, M=M, n_outputs=L, x_basis_warp=x_basis[::2], kernels=None, model_type='dynamic',
+                         ini_lengthscale=3.0, bound_lengthscale=(1.0, 20.0), ini_gamma=0.5, ini_sigma=0.5,
+                         ini_outputscale=300.0, noise_warp=0.05, bound_sigma=(1e-5, 1.0), bound_gamma=(1e-5, 1.0),
+                         bound_noise_warp=(0.005, 0.01), verbose=False, hmm_switch=True, max_models=M + 1,
+                         bayesian_params=True, inducing_points=False, estimation_limit=1, free_deg_MNIV=5)
+    seg = np.bincount(labels, minlength=M)
+    soff = np.cumsum(seg + 1) - (seg + 1)
+    eye = torch.eye(T)
+    for ld in range(L):
+        tb = wl["leads"][ld]
+        for m in range(M):
+            gp = sw.gpmodels[ld][m]
+            idx = np.nonzero(labels == m)[0]
+            rows = tb["mu"][soff[m]:soff[m] + idx.size + 1]
+            gp.f_star = [r.reshape(T, 1).clone() for r in rows]          # state i = mean after the i-th member (0: prior)
+            gp.f_star_sm = list(gp.f_star)
+            gp.cov_f_sm = [eye] * len(gp.f_star)                         # read (not used) by resample_latent_mean on the basis grid
+            gp.cov_f = gp.cov_f_sm
+            gp.C = [eye, eye]
+            gp.Sigma = [0.5 * eye, tb["Sigma"][m].clone()]               # Sigma[0]: prior (first-member jitter), Sigma[-1]: shared
+            gp.indexes = [int(i) for i in idx]
+            gp.N = int(idx.size)
+            gp.estimation_limit = 1                                      # every state uses C[-1], Sigma[-1] (GPI_model.py:646-651)
+    sw.transTheta = torch.from_numpy(np.asarray(wl["transTheta"], dtype=np.float64))
+    sw.startTheta = torch.from_numpy(np.asarray(wl["startTheta"], dtype=np.float64))
+    x_trains = torch.from_numpy(np.array([x_basis] * n_beats))
+    sw.x_train = x_trains
+    Y = wl["Y"]
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            q = torch.zeros((n_beats, M, L))
+            snr = torch.zeros((n_beats, M, L))
+            for ld in range(L):
+                for m in range(M):
+                    gp = sw.gpmodels[ld][m]
+                    q[:, m, ld] = gp.compute_sq_err_all(x_trains, Y[:, :, [ld]])
+                    snr[:, m, ld] = sw.compute_snr(Y[:, :, ld], gp)
+            tt, st_ = sw.transTheta, sw.startTheta
+            dsum = torch.log(torch.sum(torch.exp(digamma(tt[:M, :M + 1])), axis=1) + 1e-5)
+            transPi = digamma(tt[:M, :M]) - dsum[:, np.newaxis]
+            startPi = digamma(st_[:M]) - torch.log(torch.sum(torch.exp(digamma(st_[:M + 1]))) + 1e-5)
+            q_norm, _ = sw.LogLik(sw.weight_mean(q, snr))
+            alpha, margprob = sw.forward(startPi, transPi, q_norm)
+            beta = sw.backward(transPi, q_norm, margprob)
+            logresp, _ = sw.LogLik(torch.log(alpha * beta), axis=1)
+            logrespPair, _ = sw.LogLik(sw.coupled_state_coef(alpha, beta, transPi, q_norm, margprob), axis=1)
+            resp = sw._safe_exp(logresp)
+            respPair = sw._safe_exp(logrespPair)
+            startStateCount = resp[0]
+            transStateCount = torch.sum(respPair, axis=0)
+        times.append(time.perf_counter() - t0)
+    if outputs is not None:          # tests/test_bench_contract.py: the arm computes the workload's sweep, nothing else
+        outputs.update(q=q.numpy(), snr=snr.numpy(), z=torch.argmax(resp, dim=1).numpy(),
+                       transStateCount=transStateCount.numpy(), startStateCount=startStateCount.numpy())
+    return n_beats / (sum(times) / len(times)), cores, times
+
+
+def cpu_arm(n_ref, n_port, T, L, M, steps):
+    """(beats/s, cores, per-step seconds, kind, sample description): the unmodified reference when it is reachable,
+    otherwise the oracle port of its loop."""
+    try:
+        got = reference_sweep_beats_per_s(n_ref, T, L, M, steps=steps)
+    except Exception as e:           # a broken staging must not lose the line: fall back to the port, say why
+        got = None
+        sys.stderr.write(f"reference arm: the unmodified reference failed ({type(e).__name__}: {e}); timing the port\n")
+    if got is not None:
+        bps, cores, times = got
+        return bps, cores, times, "reference", (
+            f"{n_ref} beats of the same workload per step: the UNMODIFIED reference (torch CPU, oracle/refshim) -- "
+            "GPI_model.compute_sq_err_all + GPI_HDP.compute_snr per (cluster, lead), then weight_mean / LogLik / forward / "
+            "backward / coupled_state_coef / _safe_exp and the counts")
+    bps, cores, times = cpu_sweep_beats_per_s(n_port, T, L, M, steps=steps)
+    return bps, cores, times, "port", (
+        f"{n_port} beats of the same workload per step (oracle port of the reference loop: one Cholesky + cholesky_solve "
+        "per distinct cluster state, python HMM loop); the reference package itself was not reachable")
+
+
+def cpu_baseline_record(args, T, L, M):
+    bps, cores, times, kind, sample = cpu_arm(args.cpu_ref_beats, args.cpu_beats, T, L, M, steps=1)
+    return {"value": bps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + f"; {times[0]:.1f} s"}
 
 
 def run_reference_arm(args):
@@ -81,18 +190,16 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     T, L, M = CFG["T"], CFG["L"], CFG["M"]
-    # a bounded sample per step: ~12 s of host work at the default, shrunk so that K steps still end within a few minutes
-    n = max(1024, min(args.cpu_beats, (10 * args.cpu_beats // max(1, args.steps)) // 64 * 64))
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_sweep_beats_per_s(min(n, 256), T, L, M, steps=1)
-    bps, cores, times = cpu_sweep_beats_per_s(n, T, L, M, steps=max(1, args.steps))
-    sample = f"{n} beats of the same workload per step (oracle port of the reference loop: one Cholesky + cholesky_solve per distinct cluster state, python HMM loop)"
+    # a bounded sample per step (~15 s of host work at the default), shrunk so that K steps still end within a few minutes
+    shrink = lambda n: max(512, min(n, (8 * n // max(1, args.steps)) // 64 * 64))
+    bps, cores, times, kind, sample = cpu_arm(shrink(args.cpu_ref_beats), shrink(args.cpu_beats), T, L, M,
+                                              steps=max(1, args.steps))
     line = {
         "impl": "reference", "metric": METRIC, "value": bps, "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, args.steps),
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": SCALING,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(CFG["beats_per_gpu"], T, L, M), "cpu_sample_beats": n},
-        "cpu_baseline": {"value": bps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(CFG["beats_per_gpu"], T, L, M)},
+        "cpu_baseline": {"value": bps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": bps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,28 +274,64 @@ def measure_fp64_peak(torch, seconds=1.5):
     return best, sustained
 
 
-def run_ours(args):
-    if os.environ.get("HGP_BENCH_WATCHDOG"):
-        import faulthandler
-        faulthandler.dump_traceback_later(int(os.environ["HGP_BENCH_WATCHDOG"]), exit=True)
-    import torch
-    import torch.distributed as dist
-    import hdpgpc_b200 as hb
-    from hdpgpc_b200 import ops, synthetic
+def stage_breakdown(torch, ops, eng, reps=3):
+    """CUDA events between the stages of one device-resident sweep (averaged over `reps`)."""
+    marks = []
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise hb.HgpError("bench.py needs a B200; hdpgpc_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    hb.load_library()
-    T, L, M = CFG["T"], CFG["L"], CFG["M"]
-    B = args.beats or CFG["beats_per_gpu"]
+    def mark(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+
+    for _ in range(reps):
+        mark("start")
+        for ld, tb in enumerate(eng.leads):
+            ops.score_tiles(tb.Y, tb.nu, tb.Wpacked, tb.state_of, tb.factor_of_cluster, out=eng.q[ld], tile_state=tb.tile_state)
+            mark("tiles")
+            tb.snr(eng.snr[ld])
+            mark("snr")
+            tb.score_exceptions(eng.q[ld])
+            mark("pairs")
+        qbar, e, w, hm = eng.responsibilities()
+        mark("lead_weights+hmm")
+        eng.statistics(qbar, hm)
+        mark("stats")
+    torch.cuda.synchronize()
+    acc = {}
+    for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
+        if n1 != "start":
+            acc[n1] = acc.get(n1, 0.0) + a.elapsed_time(b) / reps
+    return {k: round(v, 4) for k, v in acc.items()}
+
+
+def table_stage_breakdown(torch, ops, eng, raw, reps=3):
+    """CUDA events between the kernels of the table build (EStepEngine.update_states)."""
+    acc = {}
+    for _ in range(reps):
+        for tb, t in zip(eng.leads, raw):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            Lf, info = ops.chol_batched(t["Sigma"], add_diag=t.get("add_diag"))
+            ev[1].record()
+            W = ops.tri_inverse_batched(Lf)
+            ev[2].record()
+            ops.whiten_means(t["mu"], W, tb.factor_of_state)
+            ev[3].record()
+            ops.pack_factors(W)
+            ev[4].record()
+            torch.cuda.synchronize()
+            for k, name in enumerate(("chol", "tri_inverse", "whiten_means", "pack_factors")):
+                acc[name] = acc.get(name, 0.0) + ev[k].elapsed_time(ev[k + 1]) / reps
+    return {k: round(v, 4) for k, v in acc.items()}
+
+
+def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, warmup, rank, world, local, with_clocks,
+                   with_e2e=True):
+    """One workload: device-resident sweep (`value`), table build, end-to-end call from pinned host beats."""
+    T, L, M, B = cfg["T"], cfg["L"], cfg["M"], cfg["beats_per_gpu"]
     wl = synthetic.make_workload(B, T=T, L=L, M=M, seed=1234, device="cuda", n_offset=rank * B, N_total=world * B)
-    Y_host = wl["Y"].cpu().pin_memory()                      # e2e leg: beats live in pinned host memory
+    raw = wl["leads"]                                         # (mu, Sigma, add_diag, ...) per lead: the cluster states
+    Y_host = wl["Y"].cpu().pin_memory() if with_e2e else None   # e2e leg: beats live in pinned host memory
     eng = synthetic.build_engine(wl, sharded=world > 1)       # rank r holds the r-th contiguous time slice
     assert all(tb.use_tiles for tb in eng.leads)
 
@@ -228,15 +371,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    peak_burst = peak_sust = None
-    if rank == 0 and not args.no_peak:
-        peak_burst, peak_sust = measure_fp64_peak(torch)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         sweep()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if with_clocks else None
+    if sampler is not None and rank == 0:
         sampler.start()
         time.sleep(0.25)
     launches0 = ops.launch_count()
@@ -244,45 +389,135 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         st, hm = sweep(record=True)
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
     launches = ops.launch_count() - launches0
-    ms = ev0.elapsed_time(ev1) / args.steps
+    ms = ev0.elapsed_time(ev1) / steps
     tile_ms = sum(a.elapsed_time(b) for a, b in tile_events) / max(1, len(tile_events))
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t)
+    clocks = sampler.stop(t_wall0, t_wall1) if (sampler is not None and rank == 0) else None
+    ms_max = max_over_ranks(ms)
+    acc = float((hm.z.cpu() == torch.from_numpy(wl["labels"])).double().mean())
 
-    # ---- end-to-end leg: host beats in, labels + statistics out ----
-    def e2e_step():
-        # the public end-to-end call: pinned host beats in (sliced H2D copies overlapped with scoring), labels and
-        # statistics back on the host
-        broadcast_tables()
-        st = eng.sweep_from_host(Y_host)
-        return st["z_host"], st["stats_host"]
+    # ---- table build: new cluster states -> factors, whitened means, packed factors (what the reference re-derives
+    #      inside every E-step; it is NOT part of `value`, it IS part of `value_incl_tables` and of `e2e`) ----
     for _ in range(2):
-        e2e_step()
+        eng.update_states(raw)
     barrier()
+    n_tb = max(1, min(steps, 5))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    n_e2e = max(1, min(args.steps, 5))
-    for _ in range(n_e2e):
-        z_host, stats_host = e2e_step()
+    for _ in range(n_tb):
+        eng.update_states(raw)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / n_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t)
-    h2d = Y_host.numel() * 8
-    d2h = z_host.numel() * 4 + stats_host.numel() * 8
+    eng.check_tables()
+    table_ms = max_over_ranks(e0.elapsed_time(e1) / n_tb)
 
-    acc = float((hm.z.cpu() == torch.from_numpy(wl["labels"])).double().mean())
+    out = dict(cfg=cfg, B=B, ms=ms, ms_max=ms_max, tile_ms=tile_ms, launches=int(launches), clocks=clocks, acc=acc,
+               table_ms=table_ms, eng_rounds=(eng.hmm_rounds, eng.boundary_rounds),
+               means_mb=sum(tb.nu.numel() for tb in eng.leads) * 8 / 1e6,
+               bytes_launch=B * T * 8 + B * M * 8 + B * M * 4 + eng.leads[0].mu.numel() * 8 + eng.leads[0].Wpacked.numel() * 8)
+    if rank == 0:
+        out["stages_ms"] = stage_breakdown(torch, ops, eng) if world == 1 else None
+        out["table_stages_ms"] = table_stage_breakdown(torch, ops, eng, raw) if world == 1 else None
+    barrier()
+
+    # ---- end-to-end leg: cluster states + host beats in, labels + statistics out ----
+    if with_e2e:
+        def e2e_step():
+            # the public end-to-end call: table build from (mu, Sigma), pinned host beats in (sliced H2D copies overlapped
+            # with scoring), labels and statistics back on the host
+            eng.update_states(raw)
+            broadcast_tables()
+            st_ = eng.sweep_from_host(Y_host)
+            return st_["z_host"], st_["stats_host"]
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_e2e = max(1, min(steps, 5))
+        for _ in range(n_e2e):
+            z_host, stats_host = e2e_step()
+        e1.record()
+        barrier()
+        out["e2e_ms"] = max_over_ranks(e0.elapsed_time(e1) / n_e2e)
+        out["h2d"] = Y_host.numel() * 8
+        out["d2h"] = z_host.numel() * 4 + stats_host.numel() * 8
+    del eng, wl, raw, Y_host
+    torch.cuda.empty_cache()
+    return out
+
+
+def fit_record():
+    """Wall time of the reference's own offline fit of MIT-BIH record 100 (hdpgpc/tests/test_offline.py settings, 2272
+    beats) driven through the device path (hdpgpc_b200.integration), next to the CPU time of the same fit by the
+    unmodified reference recorded with the fixture (tests/golden/fit_rec100_offline.npz, dev container).  None when the
+    reference is not staged (tools/make_ref.sh)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import numpy as np
+        from oracle import refshim                      # checker-side infrastructure: locates / imports the reference
+        if refshim.find_reference() is None:
+            return None
+        from test_reference_fit_gpu import run_on_device
+        z = np.load(os.path.join(ROOT, "tests", "golden", "fit_rec100_offline.npz"))
+        got, wall, launches, twins = run_on_device("rec100_offline")
+        return {"rec100_offline_s": round(wall, 2), "cpu_s": round(float(z["cpu_fit_seconds"]), 1),
+                "cpu_where": f"unmodified reference, dev container, {int(z['cpu_threads'])} threads (tests/golden/fit_rec100_offline.npz)",
+                "identical_labels": bool(np.array_equal(got["labels"], z["labels"])), "clusters": int(got["M"]),
+                "clusters_reference": int(z["M"]), "gpu_launches": int(launches)}
+    except Exception as e:           # the fit record is an extra: never lose the bench line over it
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def run_ours(args):
+    if os.environ.get("HGP_BENCH_WATCHDOG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["HGP_BENCH_WATCHDOG"]), exit=True)
+    import torch
+    import torch.distributed as dist
+    import hdpgpc_b200 as hb
+    from hdpgpc_b200 import ops, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise hb.HgpError("bench.py needs a B200; hdpgpc_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hb.load_library()
+    T, L, M = CFG["T"], CFG["L"], CFG["M"]
+    B = args.beats or CFG["beats_per_gpu"]
+    cfg = dict(T=T, L=L, M=M, beats_per_gpu=B)
+
+    peak_burst = peak_sust = None
+    if rank == 0 and not args.no_peak:
+        peak_burst, peak_sust = measure_fp64_peak(torch)
+
+    r = measure_config(args, torch, dist, hb, ops, synthetic, cfg, SCALING, args.steps, args.warmup, rank, world, local, True)
+    ms, ms_max, tile_ms, table_ms, e2e_ms = r["ms"], r["ms_max"], r["tile_ms"], r["table_ms"], r["e2e_ms"]
+
+    # ---- second leg: BASELINE.json configs[4] (2M beats x 256 x 128 clusters, strong scaling), 3 sweeps ----
+    cfg5 = None
+    if args.config == "cfg4" and not args.no_cfg5 and not args.beats:
+        c5 = dict(T=CFG5["T"], L=CFG5["L"], M=CFG5["M"], beats_per_gpu=CFG5["beats_total"] // world)
+        r5 = measure_config(args, torch, dist, hb, ops, synthetic, c5, "strong", 3, 3, rank, world, local, False, with_e2e=False)
+        if rank == 0:
+            fl5 = c5["beats_per_gpu"] * c5["M"] * (c5["T"] ** 2 + 3 * c5["T"])
+            peak5 = peak_sust if peak_sust else 37.0
+            cfg5 = {"workload": f"synthetic {CFG5['beats_total']} beats x {c5['T']} samples x {c5['L']} lead, {c5['M']} clusters, "
+                                f"{c5['beats_per_gpu']} beats per GPU (BASELINE.json configs[4], strong scaling)",
+                    "value": CFG5["beats_total"] / (r5["ms_max"] * 1e-3), "unit": UNIT, "ms_per_step": r5["ms_max"], "steps": 3,
+                    "frac": (fl5 / (r5["tile_ms"] * 1e-3) / 1e12) / peak5,
+                    "sweep_frac": (c5["L"] * fl5 / (r5["ms_max"] * 1e-3) / 1e12) / peak5,
+                    "tile_kernel_ms": r5["tile_ms"], "table_build_ms": r5["table_ms"], "stages_ms": r5.get("stages_ms"),
+                    "label_accuracy": r5["acc"], "hmm_repair_rounds": r5["eng_rounds"][0], "boundary_rounds": r5["eng_rounds"][1]}
 
     if rank == 0:
         flops_launch = B * M * (T * T + 3 * T)               # one tile-kernel launch = one lead plane
@@ -293,37 +528,42 @@ def run_ours(args):
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = None      # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu --set full capture
+        traffic = traffic_source = None   # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu capture
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "r01_score_tiles_ncu.json")))
             if args.config == "cfg4" and B == CFG["beats_per_gpu"]:
                 traffic = prof["dram_bytes_per_launch"]
+                traffic_source = "ncu --set full capture of this kernel at this shape, profiles/r01_score_tiles_ncu.json (not re-measured in this run)"
         except Exception:
             pass
-        bytes_launch = B * T * 8 + B * M * 8 + B * M * 4 + eng.leads[0].mu.numel() * 8 + eng.leads[0].Wpacked.numel() * 8
+        bytes_launch = r["bytes_launch"]
         cpu = None
         if not args.no_cpu:
-            bps, cores, times = cpu_sweep_beats_per_s(args.cpu_beats, T, L, M, steps=1)
-            cpu = {"value": bps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_beats} beats of the same workload, 1 sweep, {times[0]:.1f} s (oracle port of the reference loop)"}
+            cpu = cpu_baseline_record(args, T, L, M)
+        fit = None if (args.no_fit or world > 1) else fit_record()
         line = {
             "metric": METRIC, "value": world * B / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max, "higher_is_better": True, "scaling": SCALING,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(B, T, L, M), "beats_total": world * B, "l2": f"inputs_exceed_l2 (beats {B * T * L * 8 / 1e6:.0f} MB + whitened means {sum(tb.nu.numel() for tb in eng.leads) * 8 / 1e6:.0f} MB per GPU vs 126 MB L2)",
-                       "label_accuracy": acc, "hmm_repair_rounds": eng.hmm_rounds, "boundary_rounds": eng.boundary_rounds},
+            "config": {"workload": workload_name(B, T, L, M), "beats_total": world * B, "l2": f"inputs_exceed_l2 (beats {B * T * L * 8 / 1e6:.0f} MB + whitened means {r['means_mb']:.0f} MB per GPU vs 126 MB L2)",
+                       "label_accuracy": r["acc"], "hmm_repair_rounds": r["eng_rounds"][0], "boundary_rounds": r["eng_rounds"][1]},
+            "table_build_ms": table_ms, "table_build_share_of_sweep": table_ms / ms_max,
+            "value_incl_tables": world * B / ((ms_max + table_ms) * 1e-3),
+            "stages_ms": r.get("stages_ms"), "table_stages_ms": r.get("table_stages_ms"),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "score_tiles_kernel", "kernel_ms": tile_ms,
+                         "traffic": traffic, "traffic_source": traffic_source, "kernel": "score_tiles_kernel", "kernel_ms": tile_ms,
                          "kernel_share_of_step": L * tile_ms / ms, "flops_per_launch": flops_launch,
                          "peak_source": "cuBLAS DGEMM 8192^3 float64 measured in this run, sustained (MEASURED_PEAKS.json has no FP64 figure)" if peak_sust else "nominal",
                          "peak_burst": peak_burst,
                          "hbm": {"algorithmic_bytes_per_launch": bytes_launch, "achieved_gbs": bytes_launch / (tile_ms * 1e-3) / 1e9,
                                  "peak_gbs": mp.get("hbm_gbs"), "frac": (bytes_launch / (tile_ms * 1e-3) / 1e9) / mp["hbm_gbs"] if mp.get("hbm_gbs") else None}},
             "cpu_baseline": cpu,
-            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "ms_per_step": e2e_ms, "includes": "table build from (mu, Sigma) + H2D of the beats + sweep + D2H of labels / statistics"},
+            "cfg5": cfg5,
+            "fit": fit,
+            "gpu_launches": r["launches"],
+            "clocks": r["clocks"],
         }
         print(json.dumps(line))
     if world > 1:
@@ -339,9 +579,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--beats", type=int, default=0, help="beats per GPU (default: the cfg4 100000)")
-    ap.add_argument("--cpu-beats", type=int, default=8192, help="beats in the bounded CPU sample")
+    ap.add_argument("--cpu-beats", type=int, default=8192, help="beats in the bounded CPU sample (oracle port)")
+    ap.add_argument("--cpu-ref-beats", type=int, default=1024, help="beats in the bounded CPU sample (unmodified reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-peak", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the short configs[4] leg (2M beats x 128 clusters)")
+    ap.add_argument("--no-fit", action="store_true", help="skip the record-100 fit through the device path")
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"])
     args = ap.parse_args()
     if args.config == "cfg5":

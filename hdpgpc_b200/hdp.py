@@ -120,6 +120,23 @@ class LeadTables:
             self.pair_n = nz[:, 0].to(I32).contiguous()
             self.pair_m = nz[:, 1].to(I32).contiguous()
 
+    def update_states(self, mu, Sigma, add_diag=None, mu_sm=None):
+        """New cluster states on unchanged index maps (which state scores which beat, `factor_of_state`): what the
+        reference re-derives inside every E-step -- one Cholesky per distinct covariance (GPI_model._chol_spd,
+        GPI_model.py:83-87, called per group at :521-533) -- as one table build on the device: factorise, invert the
+        factors, whiten the state means with them, re-pack the factors for the tensor cores.  mu [S, T], Sigma [F, T, T],
+        add_diag [F] (the `first` jitter of the duplicated first-member factors, :527-529)."""
+        Lf, info = ops.chol_batched(Sigma, add_diag=add_diag)
+        self.W = ops.tri_inverse_batched(Lf)
+        self.mu = mu
+        if mu_sm is not None:
+            self.mu_sm = mu_sm
+        if self.use_tiles:
+            self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
+            if not self.block_path:
+                self.Wpacked = ops.pack_factors(self.W)
+        return info
+
     def score(self, out, snr_out=None):
         """q (and, when snr_out is given, the SNR statistic) for this lead plane."""
         if self.use_tiles:
@@ -246,6 +263,20 @@ class EStepEngine:
         pi, PiT, Pi, Pc = hmm_operands(transTheta, startPi, M)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
         self.pi, self.PiT, self.Pi, self.Pc = up(pi), up(PiT), up(Pi), up(Pc)
+
+    def update_states(self, tables):
+        """Table build for new cluster states (see LeadTables.update_states): `tables[ld]` = dict(mu, Sigma, add_diag
+        [, mu_sm]).  Raises LinAlgError for a covariance that is not positive definite (LAPACK-style info per matrix)."""
+        infos = [tb.update_states(t["mu"], t["Sigma"], t.get("add_diag"), t.get("mu_sm")) for tb, t in zip(self.leads, tables)]
+        bad = torch.stack([torch.count_nonzero(i) for i in infos])
+        self._table_info = bad          # checked lazily (check_tables) so that the build stays asynchronous
+        return self
+
+    def check_tables(self):
+        bad = getattr(self, "_table_info", None)
+        if bad is not None and int(bad.sum()):
+            from .model import LinAlgError
+            raise LinAlgError("linalg.cholesky: a cluster covariance is not positive-definite")
 
     # -- pieces --
     def score_all(self):
