@@ -305,23 +305,33 @@ def stage_breakdown(torch, ops, eng, reps=3):
 
 
 def table_stage_breakdown(torch, ops, eng, raw, reps=3):
-    """CUDA events between the kernels of the table build (EStepEngine.update_states)."""
+    """CUDA events between the kernels of the table build (EStepEngine.update_states: the factorisations of all leads in
+    one launch each, then whitening and packing per lead)."""
     acc = {}
+    Sig = torch.cat([t["Sigma"] for t in raw], dim=0)
+    add = torch.cat([t["add_diag"] for t in raw]) if all(t.get("add_diag") is not None for t in raw) else None
     for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        Lf, info = ops.chol_batched(Sig, add_diag=add)
+        ev[1].record()
+        W = ops.tri_inverse_batched(Lf)
+        ev[2].record()
+        off = 0
         for tb, t in zip(eng.leads, raw):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-            ev[0].record()
-            Lf, info = ops.chol_batched(t["Sigma"], add_diag=t.get("add_diag"))
-            ev[1].record()
-            W = ops.tri_inverse_batched(Lf)
-            ev[2].record()
-            ops.whiten_means(t["mu"], W, tb.factor_of_state)
-            ev[3].record()
-            ops.pack_factors(W)
-            ev[4].record()
-            torch.cuda.synchronize()
-            for k, name in enumerate(("chol", "tri_inverse", "whiten_means", "pack_factors")):
-                acc[name] = acc.get(name, 0.0) + ev[k].elapsed_time(ev[k + 1]) / reps
+            F = t["Sigma"].shape[0]
+            ops.whiten_means(t["mu"], W[off:off + F], tb.factor_of_state)
+            off += F
+        ev[3].record()
+        off = 0
+        for tb, t in zip(eng.leads, raw):
+            F = t["Sigma"].shape[0]
+            ops.pack_factors(W[off:off + F])
+            off += F
+        ev[4].record()
+        torch.cuda.synchronize()
+        for k, name in enumerate(("chol", "tri_inverse", "whiten_means", "pack_factors")):
+            acc[name] = acc.get(name, 0.0) + ev[k].elapsed_time(ev[k + 1]) / reps
     return {k: round(v, 4) for k, v in acc.items()}
 
 

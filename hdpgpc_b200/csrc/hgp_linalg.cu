@@ -137,6 +137,11 @@ chol_kernel(const double* __restrict__ Sigma, const int* __restrict__ src_idx, c
     }
 }
 
+// W = L^{-1} by blocked forward substitution on the identity.  Column blocks of the inverse are independent of one
+// another (column j of W only needs L and the rows of column j above it), so one matrix is spread over gridDim.y CTAs,
+// each owning a group of 16-column blocks: the sweep over the row blocks is the serial part, and with 8 groups per
+// 256 x 256 factor a table build of 128 factors fills the machine instead of occupying 128 of its 148 SMs for the
+// whole serial sweep.
 __global__ void __launch_bounds__(256)
 tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ Wout) {
     extern __shared__ double smem[];
@@ -149,15 +154,20 @@ tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ 
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     const int nblk = (T + NB - 1) / NB;
+    const int per = (nblk + gridDim.y - 1) / gridDim.y;
+    const int bj_lo = blockIdx.y * per, bj_hi = min(nblk, bj_lo + per);     // this CTA's column blocks
+    if (bj_lo >= nblk) return;
+    const int c_lo = bj_lo * NB, c_hi = min(T, bj_hi * NB);
 
     for (int bi = 0; bi < nblk; ++bi) {
         const int r0 = bi * NB;
         const int nb = min(NB, T - r0);
-        // zero the strict upper part of this block row (columns > r0+row)
-        for (int idx = tid; idx < nb * T; idx += 256) {
-            int i = idx / T, j = idx % T;
+        // zero the strict upper part of this block row inside the CTA's columns (columns > r0+row)
+        for (int idx = tid; idx < nb * (c_hi - c_lo); idx += 256) {
+            int i = idx / (c_hi - c_lo), j = c_lo + idx % (c_hi - c_lo);
             if (j > r0 + i) W[(int64_t)(r0 + i) * T + j] = 0.0;
         }
+        if (bi < bj_lo) continue;            // rows above the group's first diagonal block hold zeros only
         if (ty < nb && tx < nb) Lii[ty * (NB + 1) + tx] = Lm[(int64_t)(r0 + ty) * T + r0 + tx];
         __syncthreads();
         // Inv = Lii^{-1}: thread c solves column c
@@ -179,7 +189,8 @@ tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ 
             }
         }
         // R[bj] = sum_{k in [c0, r0)} L[r0+ty][k] * W[k][c0+tx]
-        for (int bj = 0; bj < bi; ++bj) {
+        const int bj_end = min(bi, bj_hi);
+        for (int bj = bj_lo; bj < bj_end; ++bj) {
             const int c0 = bj * NB;
             double acc = 0.0;
             if (ty < nb) {
@@ -189,7 +200,7 @@ tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ 
             R[(bj * NB + ty) * (NB + 1) + tx] = acc;
         }
         __syncthreads();
-        for (int bj = 0; bj < bi; ++bj) {
+        for (int bj = bj_lo; bj < bj_end; ++bj) {
             const int c0 = bj * NB;
             if (ty < nb) {
                 double acc = 0.0;
@@ -197,7 +208,7 @@ tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ 
                 W[(int64_t)(r0 + ty) * T + c0 + tx] = -acc;
             }
         }
-        if (ty < nb && tx < nb && tx <= ty) W[(int64_t)(r0 + ty) * T + r0 + tx] = Inv[ty * (NB + 1) + tx];
+        if (bi < bj_hi && ty < nb && tx < nb && tx <= ty) W[(int64_t)(r0 + ty) * T + r0 + tx] = Inv[ty * (NB + 1) + tx];
         __syncthreads();
     }
 }
@@ -283,7 +294,8 @@ extern "C" int hgp_tri_inverse_batched(const double* Lfac, int64_t F, int T, dou
         cudaError_t e = cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return hgp_status(e, "hgp_tri_inverse_batched: smem attribute");
     }
-    tri_inverse_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(Lfac, T, W);
+    const int groups = nblk >= 16 ? 8 : (nblk >= 8 ? 4 : (nblk >= 4 ? 2 : 1));
+    tri_inverse_kernel<<<dim3((unsigned)F, groups), 256, smem, (cudaStream_t)stream>>>(Lfac, T, W);
     HGP_LAUNCH_CHECK("hgp_tri_inverse_batched");
     return 0;
 }

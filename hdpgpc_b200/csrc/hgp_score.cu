@@ -632,6 +632,99 @@ whiten_means_kernel(const double* __restrict__ mu, const double* __restrict__ W,
     }
 }
 
+// The same product on the tensor cores.  The rows of a state table are grouped by cluster, so 64 consecutive states
+// almost always share one factor: nu[s0 .. s0 + 64][:] = Mu_tile W_f^T is then a 64 x T x T lower-triangular product
+// (the k loop of column block c stops at its diagonal), Mu rows as the A operand and rows of W as the (transposed) B
+// operand of DMMA.8x8x4, the next k chunk prefetched into registers under the current one.  Tiles that straddle a
+// cluster boundary (and tables with one factor per state, factor_of_state == NULL) take the row-by-row path.
+// A table build re-whitens every state mean of a sweep (cfg4: 100k states x 256^2 per lead -- 6.5 GFLOP, 3.3 ms with one
+// warp per output element); as a dense contraction it costs a fraction of a millisecond.
+__global__ void __launch_bounds__(256)
+whiten_tiles_kernel(const double* __restrict__ mu, const double* __restrict__ W, const int* __restrict__ factor_of_state,
+                    int64_t S, int T, double* __restrict__ nu) {
+    __shared__ double As[64 * 20];
+    __shared__ double Bs[64 * 20];              // [column][k]: stored and read along k, conflict-free like As
+    __shared__ int s_uni;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t s0 = (int64_t)blockIdx.x * 64;
+    const int ns = (int)hgp_min64(64, S - s0);
+    if (tid == 0) s_uni = factor_of_state != nullptr;
+    __syncthreads();
+    if (factor_of_state && tid < ns && factor_of_state[s0 + tid] != factor_of_state[s0]) s_uni = 0;
+    __syncthreads();
+    if (!s_uni) {
+        for (int sl = 0; sl < ns; ++sl) {
+            const int64_t st = s0 + sl;
+            const double* Wf = W + (int64_t)(factor_of_state ? factor_of_state[st] : st) * T * T;
+            const double* m = mu + st * T;
+            for (int r = warp; r < T; r += 8) {
+                const double* wr = Wf + (int64_t)r * T;
+                double acc = 0.0;
+                for (int k = lane; k <= r; k += 32) acc += wr[k] * m[k];
+                acc = warp_sum(acc);
+                if (lane == 0) nu[st * T + r] = acc;
+            }
+        }
+        return;
+    }
+    const double* Wf = W + (int64_t)factor_of_state[s0] * T * T;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nct = (T + 63) / 64;
+    double pa[4], pb[4];
+    for (int ct = 0; ct < nct; ++ct) {
+        const int c0 = ct * 64;
+        const int kend = min(T, c0 + 64);            // W[r][k] = 0 for k > r, r < c0 + 64
+        auto fetch = [&](int k0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = tid + u * 256;
+                const int r = idx >> 4, k = idx & 15;                  // A: 64 states x 16 k
+                pa[u] = (r < ns && k0 + k < kend) ? mu[(s0 + r) * T + k0 + k] : 0.0;
+                const int cc = idx >> 4, kb = idx & 15;                // B[kb][cc] = W[c0 + cc][k0 + kb]
+                pb[u] = (c0 + cc < T && k0 + kb < kend) ? Wf[(int64_t)(c0 + cc) * T + k0 + kb] : 0.0;
+            }
+        };
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        fetch(0);
+        for (int k0 = 0; k0 < kend; k0 += 16) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = tid + u * 256;
+                As[(idx >> 4) * 20 + (idx & 15)] = pa[u];
+                Bs[(idx >> 4) * 20 + (idx & 15)] = pb[u];
+            }
+            __syncthreads();
+            if (k0 + 16 < kend) fetch(k0 + 16);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                double a[2], bf[4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = As[(16 * wm + 8 * i + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = Bs[(32 * wn + 8 * j + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = 16 * wm + 8 * i + (lane >> 2), cc = c0 + 32 * wn + 8 * j + 2 * (lane & 3) + e;
+                    if (r < ns && cc < T) nu[(s0 + r) * T + cc] = acc[i][j][e];
+                }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // generic pair kernel: one warp per (n, m) pair, arbitrary factor per state
 // ------------------------------------------------------------------------------------------
@@ -1092,7 +1185,10 @@ extern "C" int hgp_whiten_means(const double* mu, const double* W, const int* fa
     HGP_REQUIRE(S >= 0 && T > 0 && T <= 4096, "hgp_whiten_means: bad sizes");
     if (S == 0) return 0;
     HGP_REQUIRE(S < (1ll << 31), "hgp_whiten_means: too many states for one launch");
-    whiten_means_kernel<<<(unsigned)S, 256, sizeof(double) * T, (cudaStream_t)stream>>>(mu, W, factor_of_state, T, nu);
+    if (factor_of_state && S >= 64 && !getenv("HGP_WHITEN_SCALAR"))
+        whiten_tiles_kernel<<<(unsigned)((S + 63) / 64), 256, 0, (cudaStream_t)stream>>>(mu, W, factor_of_state, S, T, nu);
+    else
+        whiten_means_kernel<<<(unsigned)S, 256, sizeof(double) * T, (cudaStream_t)stream>>>(mu, W, factor_of_state, T, nu);
     HGP_LAUNCH_CHECK("hgp_whiten_means");
     return 0;
 }

@@ -120,14 +120,17 @@ class LeadTables:
             self.pair_n = nz[:, 0].to(I32).contiguous()
             self.pair_m = nz[:, 1].to(I32).contiguous()
 
-    def update_states(self, mu, Sigma, add_diag=None, mu_sm=None):
+    def update_states(self, mu, Sigma, add_diag=None, mu_sm=None, W=None, info=None):
         """New cluster states on unchanged index maps (which state scores which beat, `factor_of_state`): what the
         reference re-derives inside every E-step -- one Cholesky per distinct covariance (GPI_model._chol_spd,
         GPI_model.py:83-87, called per group at :521-533) -- as one table build on the device: factorise, invert the
         factors, whiten the state means with them, re-pack the factors for the tensor cores.  mu [S, T], Sigma [F, T, T],
-        add_diag [F] (the `first` jitter of the duplicated first-member factors, :527-529)."""
-        Lf, info = ops.chol_batched(Sigma, add_diag=add_diag)
-        self.W = ops.tri_inverse_batched(Lf)
+        add_diag [F] (the `first` jitter of the duplicated first-member factors, :527-529).  W / info: factors already
+        inverted by the caller (EStepEngine.update_states factorises all leads in one launch)."""
+        if W is None:
+            Lf, info = ops.chol_batched(Sigma, add_diag=add_diag)
+            W = ops.tri_inverse_batched(Lf)
+        self.W = W
         self.mu = mu
         if mu_sm is not None:
             self.mu_sm = mu_sm
@@ -267,8 +270,21 @@ class EStepEngine:
     def update_states(self, tables):
         """Table build for new cluster states (see LeadTables.update_states): `tables[ld]` = dict(mu, Sigma, add_diag
         [, mu_sm]).  Raises LinAlgError for a covariance that is not positive definite (LAPACK-style info per matrix)."""
-        infos = [tb.update_states(t["mu"], t["Sigma"], t.get("add_diag"), t.get("mu_sm")) for tb, t in zip(self.leads, tables)]
-        bad = torch.stack([torch.count_nonzero(i) for i in infos])
+        # the factorisations of all leads in ONE launch each: a CTA per 256 x 256 factor is latency-bound and needs few
+        # registers, so the factors of the second lead ride along on the same SMs instead of waiting for a second wave
+        Sig = torch.cat([t["Sigma"] for t in tables], dim=0)
+        add = None
+        if any(t.get("add_diag") is not None for t in tables):
+            add = torch.cat([t["add_diag"] if t.get("add_diag") is not None
+                             else torch.zeros(t["Sigma"].shape[0], dtype=F64, device=Sig.device) for t in tables])
+        Lf, info = ops.chol_batched(Sig, add_diag=add)
+        W_all = ops.tri_inverse_batched(Lf)
+        off = 0
+        for tb, t in zip(self.leads, tables):
+            F = t["Sigma"].shape[0]
+            tb.update_states(t["mu"], None, None, t.get("mu_sm"), W=W_all[off:off + F], info=info[off:off + F])
+            off += F
+        bad = torch.count_nonzero(info).reshape(1)
         self._table_info = bad          # checked lazily (check_tables) so that the build stays asynchronous
         return self
 

@@ -305,7 +305,15 @@ def _log_sq_error(self, x_train, y, mean=None, cov=None, C=None, Sigma=None, i=N
 
 
 def _return_LDS_param_likelihood(self, first=False):
-    return _cpu(device_model(self).return_LDS_param_likelihood(first=first))
+    tw = device_model(self)
+    v = tw.return_LDS_param_likelihood(first=first)
+    if first:
+        return _cpu(v)
+    c = tw.__dict__.get("_lds_lik_host")            # host copy of the twin's cached value: one download per parameter update
+    if c is None or c[0] is not v:
+        c = (v, _cpu(v))
+        tw._lds_lik_host = c
+    return c[1]
 
 
 def _posterior_weighted(self, x_train, y, h, t=None):

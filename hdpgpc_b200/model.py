@@ -442,6 +442,7 @@ class GPI_model:
         """Call after editing the histories in place from outside the model's own methods."""
         self._tables = None
         self._qlat_stable = 0
+        self._lds_lik = None
 
     def compute_q_lat_all(self, x_trains, h_ini=1.0):
         """GPI_model.compute_q_lat_all (GPI_model.py:549-559) -> log_lat_error (:288-323): per member j the
@@ -511,8 +512,14 @@ class GPI_model:
         return d
 
     def return_LDS_param_likelihood(self, first=False):
-        """GPI_model.return_LDS_param_likelihood (GPI_model.py:459-486), first=False."""
-        return lds_param_likelihood_batch([self], first=first)[0]
+        """GPI_model.return_LDS_param_likelihood (GPI_model.py:459-486), first=False.  The value depends on the last
+        parameter set and the prior defaults only, so it is kept until a parameter update / re-initialisation (the
+        drivers ask for it inside every compute_q_elbo, GPI_HDP.py:1838-1864, far more often than parameters change)."""
+        if first:
+            return lds_param_likelihood_batch([self], first=first)[0]
+        if getattr(self, "_lds_lik", None) is None:
+            self._lds_lik = lds_param_likelihood_batch([self])[0]
+        return self._lds_lik
 
     # ---- online extras ------------------------------------------------------------------------------
     def posterior_weighted(self, x_train, y, h, t=None):
@@ -675,6 +682,7 @@ class GPI_model:
         for k in self._PAR:
             setattr(self, k, self._store[k][:n_par])
         self._tables = None
+        self._lds_lik = None
         self._qlat_dirty(nC - 2)               # members that read "the last parameter set" now read another one
 
     # ---- chain replay -------------------------------------------------------------------------------

@@ -912,6 +912,31 @@ def test_snr_tensor_core_path_vs_scalar_and_oracle(N, T, M):
         assert float(fast[n_eq, 0]) > 100.0 and abs(float(fast[n_eq, 0]) - float(want[n_eq, 0])) < 1e-6
 
 
+@pytest.mark.parametrize("T,S", [(256, 1000), (90, 333), (30, 64)])
+def test_table_build_kernels(T, S):
+    """The table build of a sweep (EStepEngine.update_states): the triangular inverse spread over column groups and the
+    tensor-core whitening of the state means, against numpy -- tiles of 64 states with one factor (tensor-core path),
+    tiles that straddle a factor change and a ragged last tile (row-by-row path)."""
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(T + S)
+    F = 5
+    Sig = random_spd(rng, F, T, cond=1e4)
+    Lf, info = ops.chol_batched(cu(Sig))
+    assert int(torch.count_nonzero(info)) == 0
+    W = ops.tri_inverse_batched(Lf)
+    for f in range(F):
+        Lr = np.linalg.cholesky(0.5 * (Sig[f] + Sig[f].T) + 1e-8 * np.mean(np.abs(np.diag(Sig[f]))) * np.eye(T))
+        Wf = W[f].cpu().numpy()
+        assert np.max(np.abs(np.triu(Wf, 1))) == 0.0
+        assert np.max(np.abs(Wf @ Lr - np.eye(T))) < 1e-9
+    mu = rng.standard_normal((S, T)) * 50.0
+    fos = np.sort(rng.integers(0, F, size=S)).astype(np.int32)            # grouped by factor like a state table
+    fos[S // 2] = (fos[S // 2] + 1) % F                                   # one stray state inside a tile
+    nu = ops.whiten_means(cu(mu), W, cu(fos).to(torch.int32)).cpu().numpy()
+    ref = np.einsum("srk,sk->sr", W.cpu().numpy()[fos], mu)
+    assert np.max(np.abs(nu - ref)) < 1e-12 * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("M", [40, 100])
 def test_snr_arbitrary_state_map(M):
     """hgp_snr_states accepts ANY snr_state_of: with a random map nearly every beat of a 64-beat tile starts a new run of
