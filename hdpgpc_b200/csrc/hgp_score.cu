@@ -644,84 +644,104 @@ whiten_tiles_kernel(const double* __restrict__ mu, const double* __restrict__ W,
                     int64_t S, int T, double* __restrict__ nu) {
     __shared__ double As[64 * 20];
     __shared__ double Bs[64 * 20];              // [column][k]: stored and read along k, conflict-free like As
-    __shared__ int s_uni;
+    __shared__ int s_run[65], s_nrun;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t s0 = (int64_t)blockIdx.x * 64;
+    // last tile first: the table ends with the duplicated first-member states, one factor each -- the slow tile must
+    // not be the tail of the launch
+    const int64_t s0 = ((int64_t)gridDim.x - 1 - blockIdx.x) * 64;
     const int ns = (int)hgp_min64(64, S - s0);
-    if (tid == 0) s_uni = factor_of_state != nullptr;
+    if (tid == 0) {                             // runs of equal factor inside the tile
+        int n = 0;
+        s_run[0] = 0;
+        for (int i = 1; i < ns; ++i)
+            if (factor_of_state[s0 + i] != factor_of_state[s0 + i - 1]) s_run[++n] = i;
+        s_run[++n] = ns;
+        s_nrun = n;
+    }
     __syncthreads();
-    if (factor_of_state && tid < ns && factor_of_state[s0 + tid] != factor_of_state[s0]) s_uni = 0;
-    __syncthreads();
-    if (!s_uni) {
-        for (int sl = 0; sl < ns; ++sl) {
+    const int nrun = s_nrun;
+    if (nrun > 4) {
+        // (nearly) one factor per state: one warp per state, four output rows in flight
+        for (int sl = warp; sl < ns; sl += 8) {
             const int64_t st = s0 + sl;
-            const double* Wf = W + (int64_t)(factor_of_state ? factor_of_state[st] : st) * T * T;
+            const double* Wf = W + (int64_t)factor_of_state[st] * T * T;
             const double* m = mu + st * T;
-            for (int r = warp; r < T; r += 8) {
-                const double* wr = Wf + (int64_t)r * T;
-                double acc = 0.0;
-                for (int k = lane; k <= r; k += 32) acc += wr[k] * m[k];
-                acc = warp_sum(acc);
-                if (lane == 0) nu[st * T + r] = acc;
+            for (int r0 = 0; r0 < T; r0 += 4) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int k = lane; k <= min(T - 1, r0 + 3); k += 32) {
+                    const double mv = m[k];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (r0 + q < T && k <= r0 + q) acc[q] += Wf[(int64_t)(r0 + q) * T + k] * mv;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+                const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+                if (lane < 4 && r0 + lane < T) nu[st * T + r0 + lane] = v;
             }
         }
         return;
     }
-    const double* Wf = W + (int64_t)factor_of_state[s0] * T * T;
     const int wm = warp >> 1, wn = warp & 1;
     const int nct = (T + 63) / 64;
     double pa[4], pb[4];
-    for (int ct = 0; ct < nct; ++ct) {
-        const int c0 = ct * 64;
-        const int kend = min(T, c0 + 64);            // W[r][k] = 0 for k > r, r < c0 + 64
-        auto fetch = [&](int k0) {
+    for (int run = 0; run < nrun; ++run) {
+        const int ra = s_run[run], rb = s_run[run + 1];       // states [ra, rb) of the tile share one factor
+        const double* Wf = W + (int64_t)factor_of_state[s0 + ra] * T * T;
+        for (int ct = 0; ct < nct; ++ct) {
+            const int c0 = ct * 64;
+            const int kend = min(T, c0 + 64);            // W[r][k] = 0 for k > r, r < c0 + 64
+            auto fetch = [&](int k0) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = tid + u * 256;
-                const int r = idx >> 4, k = idx & 15;                  // A: 64 states x 16 k
-                pa[u] = (r < ns && k0 + k < kend) ? mu[(s0 + r) * T + k0 + k] : 0.0;
-                const int cc = idx >> 4, kb = idx & 15;                // B[kb][cc] = W[c0 + cc][k0 + kb]
-                pb[u] = (c0 + cc < T && k0 + kb < kend) ? Wf[(int64_t)(c0 + cc) * T + k0 + kb] : 0.0;
-            }
-        };
-        double acc[2][4][2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        fetch(0);
-        for (int k0 = 0; k0 < kend; k0 += 16) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = tid + u * 256;
-                As[(idx >> 4) * 20 + (idx & 15)] = pa[u];
-                Bs[(idx >> 4) * 20 + (idx & 15)] = pb[u];
-            }
-            __syncthreads();
-            if (k0 + 16 < kend) fetch(k0 + 16);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                double a[2], bf[4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) a[i] = As[(16 * wm + 8 * i + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bf[j] = Bs[(32 * wn + 8 * j + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int r = 16 * wm + 8 * i + (lane >> 2), cc = c0 + 32 * wn + 8 * j + 2 * (lane & 3) + e;
-                    if (r < ns && cc < T) nu[(s0 + r) * T + cc] = acc[i][j][e];
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = tid + u * 256;
+                    const int r = idx >> 4, k = idx & 15;                  // A: 64 states x 16 k
+                    pa[u] = (r >= ra && r < rb && k0 + k < kend) ? mu[(s0 + r) * T + k0 + k] : 0.0;
+                    const int cc = idx >> 4, kb = idx & 15;                // B[kb][cc] = W[c0 + cc][k0 + kb]
+                    pb[u] = (c0 + cc < T && k0 + kb < kend) ? Wf[(int64_t)(c0 + cc) * T + k0 + kb] : 0.0;
                 }
+            };
+            double acc[2][4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            fetch(0);
+            for (int k0 = 0; k0 < kend; k0 += 16) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = tid + u * 256;
+                    As[(idx >> 4) * 20 + (idx & 15)] = pa[u];
+                    Bs[(idx >> 4) * 20 + (idx & 15)] = pb[u];
+                }
+                __syncthreads();
+                if (k0 + 16 < kend) fetch(k0 + 16);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    double a[2], bf[4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) a[i] = As[(16 * wm + 8 * i + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bf[j] = Bs[(32 * wn + 8 * j + (lane >> 2)) * 20 + 4 * ks + (lane & 3)];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 16 * wm + 8 * i + (lane >> 2), cc = c0 + 32 * wn + 8 * j + 2 * (lane & 3) + e;
+                        if (r >= ra && r < rb && cc < T) nu[(s0 + r) * T + cc] = acc[i][j][e];
+                    }
+        }
     }
 }
 

@@ -466,6 +466,37 @@ class GPI_HDP:
         elb = torch.sum(lik * frac).reshape(1)
         return elb if one_sample else elb / len(live)
 
+    # ---- data terms of GPI_HDP.compute_q_elbo (:1796-1836) and calcELBO_NonlinearTerms (:2682-2700) ----
+    def elbo_data_terms(self, q, q_lat, snr, z, zpair):
+        """Everything `compute_q_elbo` derives from per-beat quantities, on the device, for the hard assignment (z, zpair):
+
+            Q_em   = sum_n qbar[n, z_n]       (:1805,  q_bas;  qbar = weight_mean(q, snr))
+            Q_lat  = sum_n qbar_lat[n, z_n]   (:1806,  elbo_latent; qbar_lat = weight_mean(q_lat, snr))
+            frac   = column sums of the lead weights, normalised, times T   (:1813-1818)
+            elbo_LDS = sum_ld frac[ld] * full_LDS_elbo(gpmodels[ld], N_m)     (:1819-1821)
+            entropy  = calcELBO_NonlinearTerms = H[q] -- exactly 0 for one-hot responsibilities: every term of
+                       calc_Hstart / calc_Htable is 1 * log(1 + 1e-30) or 0 * log(1e-30)  (:2690-2700)
+
+        q, q_lat, snr: [N, M, L]; z, zpair int32 [N].  Both sums run in the fixed order of hgp_suffstats, so accept /
+        reject comparisons on them are reproducible.  The HDP terms (elbo_Linears, :1025-1074) are K-sized host
+        scalars and stay with the caller.  Returns a dict of float64 CUDA tensors."""
+        q_l = self._t(q).permute(2, 0, 1).contiguous()
+        ql_l = self._t(q_lat).permute(2, 0, 1).contiguous()
+        s_l = None if snr is None else self._t(snr).permute(2, 0, 1).contiguous()
+        lw = None if snr is not None else self.snr_norm
+        qbar, _, w, _ = ops.lead_weights(q_l, s_l, lw)
+        qbar_lat, _, _, _ = ops.lead_weights(ql_l, s_l, lw)
+        z = z.to(device=self.device, dtype=I32).contiguous()
+        zpair = zpair.to(device=self.device, dtype=I32).contiguous()
+        Nm, _, _, Q_em, _ = ops.suffstats(z, zpair, qbar)
+        Q_em = Q_em.clone()
+        _, _, _, Q_lat, _ = ops.suffstats(z, zpair, qbar_lat)
+        wsum = torch.sum(w, dim=0)
+        frac = wsum / torch.sum(wsum) * float(self.gpmodels[0][0].T if self.gpmodels[0] else 1)
+        lds = torch.stack([self.full_LDS_elbo(self.gpmodels[ld], Nm).reshape(()) for ld in range(self.n_outputs)])
+        return dict(Q_em=Q_em.reshape(()), Q_lat=Q_lat.clone().reshape(()), frac=frac, full_LDS=lds,
+                    elbo_LDS=torch.sum(lds * frac), entropy=torch.zeros((), dtype=F64, device=self.device), Nm=Nm)
+
     # ---- GPI_HDP.LogLik (:632-661), axis=1 ----
     def LogLik(self, logSoftEv, axis=1):
         x = self._t(logSoftEv)

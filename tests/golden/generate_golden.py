@@ -146,11 +146,11 @@ def hmm_block(sw, q, snr, prefix, out, use_saved_snr=False):
     return resp, respPair, qbar
 
 
-def offline_scenario(name, rec, n, leads, stride, n_new, full, n_explore_steps=5):
+def offline_scenario(name, rec, n, leads, stride, n_new, full, n_explore_steps=5, estimation_limit=None):
     t0 = time.time()
     data, labels = load_record(rec, n, leads, stride)
     new, new_labels = load_record(rec, n_new, leads, stride, start=n)
-    sw, x_trains, x_basis, hyper = make_model(data, n_explore_steps=n_explore_steps)
+    sw, x_trains, x_basis, hyper = make_model(data, n_explore_steps=n_explore_steps, estimation_limit=estimation_limit)
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         sw.include_batch(x_trains, data)
@@ -813,6 +813,9 @@ SCENARIOS = {
     "offline_rec102_T30_L2": lambda: offline_scenario("offline_rec102_T30_L2", "102", 48, [0, 1], 3, 24, True, 3),
     # the shipped shape (T=90, lead 0, test_offline.py settings); compact dump (checksums + last states)
     "offline_rec100_T90_L1": lambda: offline_scenario("offline_rec100_T90_L1", "100", 40, [0], 1, 24, False),
+    # the benchmarked regime (R1): finite estimation_limit -- parameter sets stop being appended after 30 members, later
+    # states score with C[-1] f_star[t] and Sigma[-1] (GPI_model.py:646-651, :1092-1099; tests/test_step.ipynb uses 30)
+    "offline_rec100_T30_L1_lim30": lambda: offline_scenario("offline_rec100_T30_L1_lim30", "100", 120, [0], 3, 24, True, 5, 30),
     "hmm_synth": hmm_synth,
     "inducing_T30": inducing,
     "online_T30": online_extras,

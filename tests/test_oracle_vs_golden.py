@@ -5,7 +5,7 @@ import pytest
 
 from oracle import hdpgpc_oracle as O
 
-OFFLINE_FULL = ["offline_rec100_T30_L1", "offline_rec102_T30_L2"]
+OFFLINE_FULL = ["offline_rec100_T30_L1", "offline_rec102_T30_L2", "offline_rec100_T30_L1_lim30"]   # lim30: estimation_limit = 30
 OFFLINE_ALL = OFFLINE_FULL + ["offline_rec100_T90_L1"]
 
 
@@ -86,8 +86,9 @@ def test_chain_replay(golden, name):
     full = f"chain_0_Sigma" in z.files
     for m in range(int(z["n_chain"])):
         pre = f"chain_{m}_"
+        lim = float(z[pre + "estimation_limit"])
         gp = O.OracleGP(z["x_basis"], z["kernel_def"], float(z["ini_sigma_def"]), float(z["ini_gamma_def"]),
-                        free_deg=int(z["free_deg_MNIV"]))
+                        free_deg=int(z["free_deg_MNIV"]), estimation_limit=None if np.isinf(lim) else lim)
         q, ql = gp.full_pass_weighted(Y[:, :, 0], z[pre + "resp"], fitted_kernel=z[pre + "kernel"])
         assert gp.indexes == [int(i) for i in z[pre + "indexes"]]
         assert rel(q, z[pre + "q"]) < 1e-8
