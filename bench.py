@@ -221,7 +221,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -393,7 +393,7 @@ def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, w
     sampler = ClockSampler(local) if with_clocks else None
     if sampler is not None and rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(1.0)      # nvidia-smi's own start-up holds the driver for a moment: keep it out of the timed region
     launches0 = ops.launch_count()
     barrier()
     t_wall0 = time.perf_counter()
@@ -462,6 +462,42 @@ def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, w
     return out
 
 
+def bind_to_gpu_numa(torch, local):
+    """Run this rank (and first-touch its pinned staging memory) on the CPU cores next to its GPU: with all ranks on one
+    NUMA node the host-to-device copies of 8 ranks share one memory controller and one root complex (round 1:
+    end-to-end weak-scaling efficiency 0.74 at 8 GPUs against 0.97 device-resident).  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{getattr(p, 'pci_domain_id', 0):08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = sorted(64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1)
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"gpu_pci": bus, "cpus_bound": len(allowed), "first_cpu": allowed[0], "last_cpu": allowed[-1]}
+        return {"gpu_pci": bus, "cpus_bound": 0, "note": "GPU-local cores not in this process's cpuset"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
+def h2d_bandwidth(torch, nbytes=256 << 20):
+    """GB/s of one pinned host -> device copy of this rank (CUDA events, best of 3)."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 def fit_record():
     """Wall time of the reference's own offline fit of MIT-BIH record 100 (hdpgpc/tests/test_offline.py settings, 2272
     beats) driven through the device path (hdpgpc_b200.integration), next to the CPU time of the same fit by the
@@ -499,6 +535,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise hb.HgpError("bench.py needs a B200; hdpgpc_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(torch, local)          # before any pinned allocation (first touch decides the NUMA node)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hb.load_library()
@@ -510,6 +547,13 @@ def run_ours(args):
     if rank == 0 and not args.no_peak:
         peak_burst, peak_sust = measure_fp64_peak(torch)
 
+    h2d_gbs = h2d_bandwidth(torch)
+    if world > 1:      # all ranks copy at once: the figure that matters for the end-to-end leg
+        dist.barrier()
+        h2d_gbs = h2d_bandwidth(torch)
+        t_ = torch.tensor([h2d_gbs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+        h2d_gbs = float(t_)
     r = measure_config(args, torch, dist, hb, ops, synthetic, cfg, SCALING, args.steps, args.warmup, rank, world, local, True)
     ms, ms_max, tile_ms, table_ms, e2e_ms = r["ms"], r["ms_max"], r["tile_ms"], r["table_ms"], r["e2e_ms"]
 
@@ -548,7 +592,7 @@ def run_ours(args):
             pass
         bytes_launch = r["bytes_launch"]
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is reported by the single-GPU run only
             cpu = cpu_baseline_record(args, T, L, M)
         fit = None if (args.no_fit or world > 1) else fit_record()
         line = {
@@ -570,6 +614,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "ms_per_step": e2e_ms, "includes": "table build from (mu, Sigma) + H2D of the beats + sweep + D2H of labels / statistics"},
+            "host": {"numa_binding_rank0": numa, "h2d_gbs_per_rank_min": h2d_gbs,
+                     "h2d_note": "pinned host -> device, 256 MiB, all ranks copying at the same time, slowest rank"},
             "cfg5": cfg5,
             "fit": fit,
             "gpu_launches": r["launches"],

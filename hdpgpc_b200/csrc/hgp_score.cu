@@ -639,7 +639,7 @@ whiten_means_kernel(const double* __restrict__ mu, const double* __restrict__ W,
 // cluster boundary (and tables with one factor per state, factor_of_state == NULL) take the row-by-row path.
 // A table build re-whitens every state mean of a sweep (cfg4: 100k states x 256^2 per lead -- 6.5 GFLOP, 3.3 ms with one
 // warp per output element); as a dense contraction it costs a fraction of a millisecond.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)      // latency-bound k loop (two barriers per 16-wide chunk): three CTAs per SM
 whiten_tiles_kernel(const double* __restrict__ mu, const double* __restrict__ W, const int* __restrict__ factor_of_state,
                     int64_t S, int T, double* __restrict__ nu) {
     __shared__ double As[64 * 20];

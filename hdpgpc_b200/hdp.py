@@ -186,7 +186,7 @@ class LeadTables:
             ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m, out=out)
 
 
-def sharded_hmm_exchange(smooth, K, rank, world, group, device):
+def sharded_hmm_exchange(smooth, K, rank, world, group, device, min_rounds=2):
     """Exact HMM smoothing over rank-sharded beats.  Every rank scans its slice from
     a guessed boundary message; the boundary messages (2K doubles per rank: alpha of the slice's last
     beat, beta (.) e of its first beat) are all-gathered; slices whose incoming message changed are
@@ -194,7 +194,9 @@ def sharded_hmm_exchange(smooth, K, rank, world, group, device):
     the incoming message, so the fixed point equals the sequential scan bit for bit.
 
     smooth(boundary_in[2K], has_prev, has_next, prev) -> result with .boundary_out[2K] (device tensor); prev is the
-    previous round's result, to be repaired in place from the new boundary instead of scanning the slice again."""
+    previous round's result, to be repaired in place from the new boundary instead of scanning the slice again.
+    min_rounds: rounds before the first convergence check (every rank with a neighbour starts from a guessed message, so
+    round 1 can never be the fixed point unless world == 1)."""
     dist = torch.distributed
     has_prev, has_next = rank > 0, rank < world - 1
     bin_ = torch.empty(2 * K, dtype=F64, device=device)
@@ -213,10 +215,13 @@ def sharded_hmm_exchange(smooth, K, rank, world, group, device):
         if has_next:
             new_in[K:] = gathered[rank + 1, K:]
         changed = (new_in.view(torch.int64) != bin_.view(torch.int64)).any().to(torch.int32).reshape(1)
-        dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=group)
         rounds += 1
-        if int(changed) == 0:
-            return hm, rounds
+        # The first exchange always moves the boundary away from the guess, so its verdict is known without asking:
+        # the flag is reduced and read on the host (one synchronisation) from the second round on only.
+        if rounds >= min_rounds:
+            dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=group)
+            if int(changed) == 0:
+                return hm, rounds
         bin_ = new_in
         if rounds > world + 2:
             raise HgpError("sharded HMM boundary exchange did not converge")
