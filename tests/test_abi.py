@@ -34,6 +34,25 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert exported == syms, "library exports symbols the header does not declare (or vice versa)"
 
 
+def test_chain_desc_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of hgp_chain_desc (copied byte for byte to the device by ops.chain_run) against the header as a C
+    compiler lays it out: size and the offset of every field -- a header edit that moves a pointer must fail here, not
+    make the chain kernel follow a corrupted pointer."""
+    from hdpgpc_b200 import _lib
+    fields = [n for n, _ in _lib.ChainDesc._fields_]
+    src = tmp_path / "offsets.c"
+    prints = "\n".join(f'    printf("{n} %zu\\n", offsetof(hgp_chain_desc, {n}));' for n in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hdpgpc_b200.h"\nint main(void) {\n'
+                   + prints + '\n    printf("sizeof %zu\\n", sizeof(hgp_chain_desc));\n    return 0;\n}\n')
+    exe = tmp_path / "offsets"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(_lib.ChainDesc)
+    for n in fields:
+        assert int(out[n]) == getattr(_lib.ChainDesc, n).offset, n
+    assert len(out) == len(fields) + 1        # no field of the header is missing from the mirror (sizes agree as well)
+
+
 def test_library_is_sm100a_with_tensor_and_tma_sass():
     import hdpgpc_b200
     path = hdpgpc_b200.build()

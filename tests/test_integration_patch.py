@@ -50,11 +50,12 @@ def test_patch_applies_fails_loudly_and_restores(ref):
     originals_h = {n: getattr(hdp_mod.GPI_HDP, n) for n in hgi._PATCHES["GPI_HDP"]}
     patched = hgi.enable(gm.GPI_model, hdp_mod.GPI_HDP)
     try:
-        assert set(patched) == {f"GPI_model.{n}" for n in originals} | {f"GPI_HDP.{n}" for n in originals_h}
+        assert set(patched) == {f"{cls}.{n}" for cls, table in hgi._PATCHES.items() for n in table}
         for n, f in originals.items():
             assert getattr(gm.GPI_model, n) is not f
         # everything outside the seam is untouched: the VI control flow stays the reference's
-        for n in ("include_batch", "estimate_q_all", "variational_local_terms_batch", "compute_q_elbo"):
+        # (include_batch only gains a keyword shim: tests/test_offline.py calls it with `with_warp=`)
+        for n in ("include_sample", "estimate_q_all", "variational_local_terms_batch", "compute_q_elbo"):
             assert getattr(hdp_mod.GPI_HDP, n).__module__ == hdp_mod.GPI_HDP.__module__
         if not torch.cuda.is_available():
             with pytest.raises(hb.HgpError):          # no device -> loud failure, never a silent CPU path
