@@ -211,40 +211,101 @@ def run_reference_arm(args):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and clock-event reasons DURING the timed region -- the fields of the profiling recipe's nvidia-smi
+    clocks line, read in-process through NVML (nvidia-ml-py) every 50 ms.  Round 2 found that spawning `nvidia-smi -lms`
+    next to the timed region is itself a disturbance: on a fresh box its start-up (NVML init, enumeration of 8 GPUs) can
+    take longer than the second it was given and then holds the driver while the sweeps launch -- ms_per_step read 28.8
+    to 40.3 ms from run to run with the tile kernel at 13.2 ms every time.  NVML is initialised before the warm-up and a
+    query is a few microseconds; nvidia-smi stays as the fallback (started before the warm-up, first row awaited)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
+    def __init__(self, torch, gpu_index):
+        self.rows = []            # (t, sm_mhz, sm_max_mhz, power_w, [reasons])
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            p = torch.cuda.get_device_properties(gpu_index)
+            bus = f"{getattr(p, 'pci_domain_id', 0):08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self._sample()        # first query (lazy initialisation inside the library) well before the timed region
+            self.rows.clear()
+        except Exception:
+            self.nvml = None
+            self.gpu = gpu_index
+
+    def _sample(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        names = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            pw = 0.0
+        self.rows.append((time.perf_counter(), mhz, self.max_mhz, pw, [nm for nm, bit in names if r & bit]))
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 9:
+                try:
+                    self.rows.append((time.perf_counter(), float(c[1]), float(c[2]), float(c[3]),
+                                      [nm for nm, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
+                except ValueError:
+                    pass
 
     def start(self):
+        """Call BEFORE the warm-up sweeps; returns once sampling is under way."""
+        if self.nvml is not None:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th = threading.Thread(target=self._read_smi, daemon=True)
             self.th.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 20.0:      # start-up over before anything is timed
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
-
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        self._stop.set()
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        elif self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
+        else:
+            self.th.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or list(self.rows)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows)}
+        sm = sorted(r[1] for r in rows)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][2], "reasons": sorted({n for r in rows for n in r[4]}),
+                "samples": len(rows), "power_w_max": max(r[3] for r in rows),
+                "source": "NVML in-process, 50 ms" if self.proc is None else "nvidia-smi -lms 200"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -310,27 +371,32 @@ def table_stage_breakdown(torch, ops, eng, raw, reps=3):
     acc = {}
     Sig = torch.cat([t["Sigma"] for t in raw], dim=0)
     add = torch.cat([t["add_diag"] for t in raw]) if all(t.get("add_diag") is not None for t in raw) else None
-    for _ in range(reps):
+    for rep in range(reps + 1):          # rep 0 is a warm-up: it allocates the outputs (cudaMalloc stalls between the events)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
         Lf, info = ops.chol_batched(Sig, add_diag=add)
         ev[1].record()
         W = ops.tri_inverse_batched(Lf)
         ev[2].record()
-        off = 0
+        off, packed = 0, []
         for tb, t in zip(eng.leads, raw):
             F = t["Sigma"].shape[0]
-            ops.whiten_means(t["mu"], W[off:off + F], tb.factor_of_state)
+            packed.append(ops.pack_factors(W[off:off + F]))
             off += F
         ev[3].record()
         off = 0
-        for tb, t in zip(eng.leads, raw):
+        for tb, t, Wp in zip(eng.leads, raw, packed):
             F = t["Sigma"].shape[0]
-            ops.pack_factors(W[off:off + F])
+            if tb._whiten_plan is not None:
+                ops.whiten_means_tiles(t["mu"], W[off:off + F], Wp, tb.factor_of_state, tb._whiten_plan)
+            else:
+                ops.whiten_means(t["mu"], W[off:off + F], tb.factor_of_state)
             off += F
         ev[4].record()
         torch.cuda.synchronize()
-        for k, name in enumerate(("chol", "tri_inverse", "whiten_means", "pack_factors")):
+        if rep == 0:
+            continue
+        for k, name in enumerate(("chol", "tri_inverse", "pack_factors", "whiten_means")):
             acc[name] = acc.get(name, 0.0) + ev[k].elapsed_time(ev[k + 1]) / reps
     return {k: round(v, 4) for k, v in acc.items()}
 
@@ -387,13 +453,12 @@ def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, w
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    sampler = ClockSampler(torch, local) if (with_clocks and rank == 0) else None
+    if sampler is not None:
+        sampler.start()      # before the warm-up: whatever the sampler costs to start is over when the timed region begins
     for _ in range(max(3, warmup)):
         sweep()
     barrier()
-    sampler = ClockSampler(local) if with_clocks else None
-    if sampler is not None and rank == 0:
-        sampler.start()
-        time.sleep(1.0)      # nvidia-smi's own start-up holds the driver for a moment: keep it out of the timed region
     launches0 = ops.launch_count()
     barrier()
     t_wall0 = time.perf_counter()
@@ -407,7 +472,7 @@ def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, w
     launches = ops.launch_count() - launches0
     ms = ev0.elapsed_time(ev1) / steps
     tile_ms = sum(a.elapsed_time(b) for a, b in tile_events) / max(1, len(tile_events))
-    clocks = sampler.stop(t_wall0, t_wall1) if (sampler is not None and rank == 0) else None
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
     ms_max = max_over_ranks(ms)
     acc = float((hm.z.cpu() == torch.from_numpy(wl["labels"])).double().mean())
 

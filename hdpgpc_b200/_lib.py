@@ -25,6 +25,7 @@ PROTOTYPES = {
     "hgp_tile_beats": (_int, []),
     "hgp_tile_uniform_states": (_int, [_p, _i64, _int, _p, _p]),
     "hgp_whiten_means": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
+    "hgp_whiten_means_tiles": (_int, [_p, _p, _p, _p, _i64, _int, _p, _i64, _p, _i64, _p, _p]),
     "hgp_score_tiles": (_int, [_p, _i64, _int, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p]),
     "hgp_score_blocks": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p]),
     "hgp_score_pairs": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _i64, _p, _p]),
@@ -47,6 +48,8 @@ PROTOTYPES = {
     "hgp_chain_rts_cache_doubles": (_i64, [_int, _int]),
     "hgp_chain_small_path": (_int, [_int]),
     "hgp_chain_run": (_int, [_p, _int, _int, _p]),
+    "hgp_chain_pipeline_ctas": (_int, []),
+    "hgp_chain_run_ex": (_int, [_p, _int, _int, _int, _p]),
     "hgp_la_op": (_int, [_int, _p, _p, _p, _p, _int, _p, _p]),
     "hgp_pred_dist_work_doubles": (_i64, [_i64, _int, _int]),
     "hgp_pred_dist_inducing": (_int, [_p, _int, _p, _i64, _int, _p, _p, _p, _p, _i64, _dbl, _dbl, _dbl, _p, _p, _p, _p, _p]),

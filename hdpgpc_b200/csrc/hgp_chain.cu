@@ -512,6 +512,351 @@ chain_kernel_small(const hgp_chain_desc* __restrict__ descs, int T) {
     if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
 }
 
+// ======================================================================================================
+// The same small-system chain as a PIPELINE over a thread-block cluster of four CTAs (one SM each) per chain.
+// Real fits have a handful of long chains (MIT-BIH record 100: two chains, one of 2271 members), so one CTA per chain
+// leaves 146 SMs idle while a member costs ~26 dependent products and 6 factorisations.  The member step is not one
+// dependency chain, though:
+//   K  (rank 0)  Kalman update: predict P, gain K, new mean m+ (published early), then the Joseph-form covariance;
+//   J  (rank 1)  pair-smoother gain J = S0 A^T P^-1 as soon as P exists -- concurrently with the Kalman gain -- and the
+//                smoothed mean of the previous state once m+ is there;
+//   MI (rank 2)  MNIW posterior over (A, Gamma): its first factorisation, Sinv and m_mean Sinv depend on the PREVIOUS
+//                step only and are done before the step's data arrive; the rank-1 terms, the second factorisation and
+//                the two triangular products follow the smoothed mean;
+//   MO (rank 3)  the same for (C, Sigma), which needs m+ only.
+// The MNIW steps read MEANS only, so the Joseph form (five products) runs beside them, and the pair smoother's covariance
+// -- overwritten by the full RTS pass whenever that pass follows (phase bit 3) -- is skipped in that case.  The critical
+// path of a member drops from 26 products + 6 factorisations to 8 products + 2 factorisations.
+// The CTAs hand matrices over through global memory (L2) and monotone flags (st.release.gpu / ld.acquire.gpu, value =
+// member count); all cross-CTA reads use ld.global.cg.  A cluster launch guarantees that the four CTAs are co-resident,
+// so spinning on a flag cannot deadlock.  NCTA = 1 runs the four roles one after the other in one CTA (same code, flags
+// compiled out).  Only whole member steps (phases 7 or 15); the online single-phase calls stay on chain_kernel_small.
+constexpr int PF_P = 0, PF_M = 1, PF_S = 2, PF_F0 = 3, PF_JD = 4, PF_A = 5, PF_C = 6, PF_II = 7, PF_IO = 8;
+constexpr int PI_INFO_I = 16, PI_INFO_O = 17, PI_FAIL = 18;
+constexpr int PIPE_FLAG_INTS = 32;
+constexpr int PIPE_MATS = 26;
+
+template <bool MULTI>
+__device__ __forceinline__ void pipe_signal(int* flags, int f, int v) {
+    __syncthreads();
+    if (MULTI && threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + f), "r"(v) : "memory");
+    }
+}
+template <bool MULTI>
+__device__ __forceinline__ void pipe_wait(const int* flags, int f, int v) {
+    if (MULTI) {
+        if (threadIdx.x == 0) {
+            int cur;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cur) : "l"(flags + f) : "memory");
+            } while (cur < v);
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ int pipe_read(const int* flags, int i) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+    return v;
+}
+
+// First half of matrix_normal_inv_wishart.posterior (GPI_model.py:1300-1344): everything that depends on the
+// distribution alone.  Sinv -> Ga, m_mean Sinv -> Gd, Gc scratch.
+__device__ __noinline__ int pipe_mniw_prep(SlCtx& c, Mniw d, int T, double* Ga, double* Gc, double* Gd) {
+    const double jitter = 1e-2 * fmax(small_mean_abs_diag(d.scale, T, c), HGP_EPS);
+    const int info = sl_cholinv(c, Gc, d.m_r_cov, jitter);              // Ls^{-1}
+    if (info) return info;
+    SlEpi e;
+    sl_gemm(c, Ga, Gc, 1, Gc, 0, e, SL_TRI_A | SL_TRI_B);               // Sinv = Ls^{-T} Ls^{-1}
+    sl_gemm(c, Gd, d.m_mean, 0, Ga, 0, e);                              // m_mean Sinv
+    return 0;
+}
+// Second half: S2 = Sinv + y2 y2^T -> Ga, S1 = m_mean Sinv + y1 y2^T -> Gd, part_mean = S1 (sym(S2) + 1e-8 I)^{-1} -> Gb.
+__device__ __noinline__ int pipe_mniw_finish(SlCtx& c, const double* y1, const double* y2, int T, double* Ga, double* Gb,
+                                             double* Gc, double* Gd, double* Ge) {
+    const int n = T * T;
+    sl_invalidate(c, Ga);
+    sl_invalidate(c, Gd);
+    for (int i = threadIdx.x; i < n; i += SL_THREADS) {
+        const double a = __ldcg(y2 + i / T), b = __ldcg(y2 + i % T);
+        Ga[i] += a * b;
+        Gd[i] += __ldcg(y1 + i / T) * b;
+    }
+    __syncthreads();
+    const int info = sl_cholinv(c, Gc, Ga, 1e-8);                       // chol(sym(S2) + 1e-8 I)^{-1}
+    if (info) return info;
+    SlEpi e;
+    sl_gemm(c, Ge, Gd, 0, Gc, 1, e, SL_TRI_B);                          // S1 L2^{-T}
+    sl_gemm(c, Gb, Ge, 0, Gc, 0, e, SL_TRI_B);                          // part_mean = S1 S2^{-1}
+    return 0;
+}
+__device__ __noinline__ void pipe_mniw_commit(SlCtx& c, Mniw d, const double* y1, const double* y2, int T, const double* S2,
+                                              const double* part) {
+    const int n = T * T;
+    const double n0 = *d.n0;
+    const double a = (n0 - 2.0), den = (n0 + 1.0) - 2.0;
+    sl_invalidate(c, d.m_mean); sl_invalidate(c, d.scale); sl_invalidate(c, d.m_r_cov);
+    for (int i = threadIdx.x; i < n; i += SL_THREADS) {
+        const int r = i / T, cc = i % T;
+        d.m_mean[i] = (a * d.m_mean[i] + part[i]) / den;
+        const double e_r = __ldcg(y1 + r) - __ldcg(y2 + r), e_c = __ldcg(y1 + cc) - __ldcg(y2 + cc);
+        d.scale[i] = (a * d.scale[i] + e_r * e_c) / den;
+        d.m_r_cov[i] = S2[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *d.n0 = n0 + 1.0;
+    __syncthreads();
+}
+
+template <int NCTA>
+__global__ void __launch_bounds__(SL_THREADS, 1)
+chain_kernel_pipe(const hgp_chain_desc* __restrict__ descs, int T) {
+    constexpr bool MULTI = NCTA > 1;
+    __shared__ SlCtx c;
+    sl_init(c, T);
+    int rank = 0, chain = blockIdx.x;
+    if (MULTI) {
+        asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        asm("mov.u32 %0, %%clusterid.x;" : "=r"(chain));
+    }
+    const hgp_chain_desc d = descs[chain];
+    const bool rK = !MULTI || rank == 0, rJ = !MULTI || rank == 1, rI = !MULTI || rank == 2, rO = !MULTI || rank == 3;
+    const int n = T * T;
+    const int64_t tt = (int64_t)T * T;
+    double* G[PIPE_MATS];
+    for (int i = 0; i < PIPE_MATS; ++i) G[i] = d.work + i * tt;
+    double* v0 = d.work + PIPE_MATS * tt; double* v1 = v0 + T; double* vj = v1 + T;
+    int* flags = reinterpret_cast<int*>(d.work + PIPE_MATS * tt + 8 * (int64_t)T);
+    if (MULTI) {
+        if (rank == 0 && threadIdx.x < PIPE_FLAG_INTS) flags[threadIdx.x] = 0;
+        __threadfence();
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    Mniw mi{d.int_m_mean, d.int_m_r_cov, d.int_scale, d.int_n0};
+    Mniw mo{d.obs_m_mean, d.obs_m_r_cov, d.obs_scale, d.obs_n0};
+    const int n_tot = d.start_members + d.n_members;
+    double* Ph = d.rts_cache;                                            // [n_tot + 1][T][T]  P_s
+    double* Jh = Ph ? Ph + (int64_t)(n_tot + 1) * tt : nullptr;          //                    J_s
+    double* Vh = Ph ? Jh + (int64_t)(n_tot + 1) * tt : nullptr;          // [n_tot + 1][T]     A m_s
+    const int phases = d.phases ? d.phases : 15;
+    if ((phases & 7) != 7) {                                             // whole member steps only (host side checks as well)
+        if (rK && threadIdx.x == 0) { d.status[0] = -2; d.status[1] = d.start_params + 1; }
+        return;
+    }
+    const bool rts = (phases & 8) != 0;
+    int fail = 0;
+    int N = d.start_members;
+    int p = d.start_params;
+    for (int k = 0; k < d.n_members; ++k) {
+        const int s = d.start_members + k;
+        const int kv = k + 1;
+        const double* A = d.A + p * tt;
+        const double* Gm = d.Gamma + p * tt;
+        const double* C = d.C + p * tt;
+        const double* R = d.Sigma + p * tt;
+        const double* y = d.Y + (int64_t)d.member_beats[k] * T;
+        double* m_new = d.f_star + (int64_t)(s + 1) * T;
+        double* S_new = d.cov_f + (s + 1) * tt;
+        const bool prior = d.first_is_prior && s == 0;
+        double* Pc = Ph ? Ph + s * tt : G[10];
+        double* Am = Vh ? Vh + (int64_t)s * T : v0;
+        double* Jc = Jh ? Jh + s * tt : G[13];
+        N += 1;
+        const bool smooth = N > 1;
+        const bool below = d.estimation_limit <= 0 || N < d.estimation_limit;
+        const bool mniw = smooth && below;
+        // ---------------- K: Kalman update (GPI.py:104-150) ----------------
+        if (rK) {
+            pipe_wait<MULTI>(flags, PF_A, k);                            // parameter set p is complete
+            pipe_wait<MULTI>(flags, PF_C, k);
+            pipe_wait<MULTI>(flags, PF_JD, k);                           // the smoother has read the previous step's G0, P, A m
+            const double* m = d.f_star_sm + (int64_t)s * T;
+            const double* Sg = d.cov_f_sm + s * tt;
+            sl_gemv(Am, A, m, T, 0.0, nullptr);                          // A m
+            const double* P;
+            SlEpi e;
+            if (prior) {
+                P = Sg;                                                  // P_t = cov_prior; f* = 0; R = r_first I
+                for (int i = threadIdx.x; i < T; i += SL_THREADS) v1[i] = y[i];
+                __syncthreads();
+                sl_gemm(c, G[2], C, 0, P, 0, e);                         // C P
+                SlEpi es;
+                es.diag_add = d.r_first;
+                sl_gemm(c, G[3], G[2], 0, C, 1, es);                     // S = C P C^T + r I
+            } else {
+                small_predict(c, G[0], Pc, A, Gm, Sg);                   // G0 = A Sigma, P = A Sigma A^T + Gamma
+                pipe_signal<MULTI>(flags, PF_P, kv);
+                P = Pc;
+                sl_gemv(vj + T, C, Am, T, 0.0, nullptr);                 // f* = C A m
+                for (int i = threadIdx.x; i < T; i += SL_THREADS) v1[i] = y[i] - vj[T + i];
+                __syncthreads();
+                sl_gemm(c, G[2], C, 0, P, 0, e);                         // C P
+                SlEpi es;
+                es.beta = 1.0; es.D = R;
+                sl_gemm(c, G[3], G[2], 0, C, 1, es);                     // S = C P C^T + R
+            }
+            small_gain(c, G[6], G[3], G[2], G[4], G[5]);                 // K = P C^T S^{-1}
+            sl_gemv(m_new, G[6], v1, T, 1.0, Am);                        // m+ = A m + K (y - f*)
+            sl_copy(d.f_star_sm + (int64_t)(s + 1) * T, m_new, T);
+            pipe_signal<MULTI>(flags, PF_M, kv);
+            // Joseph form: (I - K C) P (I - K C)^T + K R K^T
+            SlEpi ei;
+            ei.alpha = -1.0; ei.diag_add = 1.0;
+            sl_gemm(c, G[7], G[6], 0, C, 0, ei);                         // I - K C
+            sl_gemm(c, G[8], G[7], 0, P, 0, e);                          // (I - K C) P
+            sl_gemm(c, G[9], G[8], 0, G[7], 1, e);                       // ... (I - K C)^T
+            SlEpi ej;
+            ej.beta = 1.0; ej.D = G[9];
+            if (prior) {
+                ej.alpha = d.r_first;
+                sl_gemm(c, S_new, G[6], 0, G[6], 1, ej, 0, d.cov_f_sm + (s + 1) * tt);      // + r K K^T
+            } else {
+                sl_gemm(c, G[5], G[6], 0, R, 0, e);                      // K R
+                sl_gemm(c, S_new, G[5], 0, G[6], 1, ej, 0, d.cov_f_sm + (s + 1) * tt);      // + K R K^T
+            }
+            pipe_signal<MULTI>(flags, PF_S, kv);
+        }
+        // ---------------- J: pair smoother (GPI_model.py:705-716, GPI.py:294-299) ----------------
+        if (rJ) {
+            if (smooth) {
+                const double* m0 = d.f_star + (int64_t)s * T;
+                const double* S0 = d.cov_f + s * tt;
+                pipe_wait<MULTI>(flags, PF_P, kv);
+                small_gain(c, Jc, Pc, G[0], G[11], G[12]);               // J = S0 A^T P^{-1}
+                pipe_wait<MULTI>(flags, PF_M, kv);
+                for (int i = threadIdx.x; i < T; i += SL_THREADS) vj[i] = __ldcg(m_new + i) - __ldcg(Am + i);
+                __syncthreads();
+                sl_gemv(d.f_star_sm + (int64_t)s * T, Jc, vj, T, 1.0, m0);   // m0 + J (m1 - A m0)
+                pipe_signal<MULTI>(flags, PF_F0, kv);
+                if (!rts) {                                              // the full RTS pass would overwrite it
+                    pipe_wait<MULTI>(flags, PF_S, kv);
+                    sl_invalidate(c, G[14]);
+                    sl_axpby(G[14], 1.0, S_new, -1.0, Pc, n);            // S1 - P
+                    SlEpi e;
+                    sl_gemm(c, G[15], Jc, 0, G[14], 0, e);               // J (S1 - P)
+                    SlEpi es;
+                    es.beta = 1.0; es.D = S0;
+                    sl_gemm(c, d.cov_f_sm + s * tt, G[15], 0, Jc, 1, es);    // S0 + J (S1 - P) J^T
+                }
+            }
+            pipe_signal<MULTI>(flags, PF_JD, kv);
+        }
+        // ---------------- MI / MO: MNIW step (GPI_model.py:966-1101) ----------------
+        const double* f1 = d.f_star_sm + (int64_t)(s + 1) * T;
+        const double* f0 = d.f_star_sm + (int64_t)s * T;
+        int i1 = 0, i2 = 0;
+        if (rI && mniw) {
+            i1 = pipe_mniw_prep(c, mi, T, G[16], G[18], G[19]);
+            pipe_wait<MULTI>(flags, PF_F0, kv);
+            pipe_wait<MULTI>(flags, PF_M, kv);
+            if (!i1) i1 = pipe_mniw_finish(c, f1, f0, T, G[16], G[17], G[18], G[19], G[20]);
+            if (MULTI) {
+                if (threadIdx.x == 0) flags[PI_INFO_I] = i1;
+                pipe_signal<MULTI>(flags, PF_II, kv);
+            }
+        }
+        if (rO && mniw) {
+            i2 = pipe_mniw_prep(c, mo, T, G[21], G[23], G[24]);
+            pipe_wait<MULTI>(flags, PF_M, kv);
+            if (!i2) i2 = pipe_mniw_finish(c, y, f1, T, G[21], G[22], G[23], G[24], G[25]);
+            if (MULTI) {
+                if (threadIdx.x == 0) flags[PI_INFO_O] = i2;
+                pipe_signal<MULTI>(flags, PF_IO, kv);
+            }
+        }
+        if (MULTI && mniw) {                                             // a failure on either side keeps BOTH (:1068-1071)
+            if (rI) { pipe_wait<MULTI>(flags, PF_IO, kv); i2 = pipe_read(flags, PI_INFO_O); }
+            if (rO) { pipe_wait<MULTI>(flags, PF_II, kv); i1 = pipe_read(flags, PI_INFO_I); }
+        }
+        if (mniw && (i1 || i2) && !fail) fail = k + 1;
+        const double fa = d.annealing ? 1.0 / ((double)N * (double)N) : 0.0;
+        if (rI) {
+            if (mniw && !(i1 || i2)) pipe_mniw_commit(c, mi, f1, f0, T, G[16], G[17]);
+            if (below) {
+                double* An = d.A + (p + 1) * tt; double* Gn = d.Gamma + (p + 1) * tt;
+                const double gi = *d.int_n0;
+                for (int i = threadIdx.x; i < n; i += SL_THREADS) {
+                    An[i] = d.int_m_mean[i];
+                    const double g = (N > 1) ? d.int_scale[i] * gi / (gi - 2.0) : Gm[i];
+                    Gn[i] = g + fa * d.Gamma[i];          // + Gamma[0] / N^2
+                }
+            }
+            pipe_signal<MULTI>(flags, PF_A, kv);
+        }
+        if (rO) {
+            if (mniw && !(i1 || i2)) pipe_mniw_commit(c, mo, y, f1, T, G[21], G[22]);
+            if (below) {
+                double* Cn = d.C + (p + 1) * tt; double* Sn = d.Sigma + (p + 1) * tt;
+                const double go = *d.obs_n0;
+                for (int i = threadIdx.x; i < n; i += SL_THREADS) {
+                    Cn[i] = d.obs_m_mean[i];
+                    const double sg = (N > 1) ? d.obs_scale[i] * go / (go - 2.0) : R[i];
+                    Sn[i] = sg + fa * d.Sigma[i];         // + Sigma[0] / N^2
+                }
+            }
+            pipe_signal<MULTI>(flags, PF_C, kv);
+        }
+        if (below) p += 1;
+    }
+    // ---------------- all roles join; rank 0 goes on alone ----------------
+    if (MULTI) {
+        const int fin = d.n_members + 1;
+        if (rI) { if (threadIdx.x == 0) flags[PI_FAIL] = fail; pipe_signal<MULTI>(flags, PF_A, fin); }
+        if (rO) pipe_signal<MULTI>(flags, PF_C, fin);
+        if (rJ) pipe_signal<MULTI>(flags, PF_JD, fin);
+        if (!rK) return;
+        pipe_wait<MULTI>(flags, PF_A, fin);
+        pipe_wait<MULTI>(flags, PF_C, fin);
+        pipe_wait<MULTI>(flags, PF_JD, fin);
+        fail = pipe_read(flags, PI_FAIL);
+    }
+    // ---------------- full RTS pass (GPI_model.py:687-703, GPI.py:262-270) ----------------
+    const int Tn = n_tot;
+    const int nA = p;
+    if (!rts) {
+        if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
+        return;
+    }
+    if (Tn >= 1) {
+        sl_copy(d.f_star_sm + (int64_t)Tn * T, d.f_star + (int64_t)Tn * T, T);
+        sl_invalidate(c, d.cov_f_sm + Tn * tt);
+        sl_copy(d.cov_f_sm + Tn * tt, d.cov_f + Tn * tt, n);
+    }
+    const bool cached = Ph != nullptr && d.start_members == 0;
+    for (int t = Tn - 2; t >= 0; --t) {
+        const int i = t + 1;                                            // state index
+        const int ia = (t < nA ? t : nA - 1) + 1;
+        const double* A = d.A + ia * tt;
+        const double* Gm = d.Gamma + ia * tt;
+        const double* mt = d.f_star + (int64_t)i * T;
+        const double* St = d.cov_f + i * tt;
+        const double* mn = d.f_star_sm + (int64_t)(i + 1) * T;
+        const double* Sn = d.cov_f_sm + (i + 1) * tt;
+        const double *Pt, *Jt, *Amt;
+        if (cached) {                                                   // the forward pass left P_i, J_i and A m_i behind
+            Pt = Ph + i * tt; Jt = Jh + i * tt; Amt = Vh + (int64_t)i * T;
+        } else {
+            sl_gemv(v0, A, mt, T, 0.0, nullptr);
+            small_predict(c, G[0], G[1], A, Gm, St);
+            small_gain(c, G[6], G[1], G[0], G[4], G[5]);
+            Pt = G[1]; Jt = G[6]; Amt = v0;
+        }
+        for (int j = threadIdx.x; j < T; j += SL_THREADS) vj[j] = mn[j] - __ldcg(Amt + j);
+        __syncthreads();
+        sl_gemv(d.f_star_sm + (int64_t)i * T, Jt, vj, T, 1.0, mt);
+        sl_invalidate(c, G[7]);
+        sl_axpby(G[7], 1.0, Sn, -1.0, Pt, n);
+        SlEpi e;
+        sl_gemm(c, G[8], Jt, 0, G[7], 0, e);
+        SlEpi es;
+        es.beta = 1.0; es.D = St;
+        sl_gemm(c, d.cov_f_sm + i * tt, G[8], 0, Jt, 1, es);
+    }
+    if (threadIdx.x == 0) { d.status[0] = fail; d.status[1] = p + 1; }
+}
+
 // unit-test hook for the shared-memory routines
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sl_op_kernel(int op, double* A, double* B, double* Cm, int T, int* info) {
@@ -570,11 +915,46 @@ la_op_kernel(int op, double* A, double* B, double* C, int* piv, int T, int* info
 }  // namespace
 
 extern "C" int64_t hgp_chain_desc_bytes(void) { return (int64_t)sizeof(hgp_chain_desc); }
-extern "C" int64_t hgp_chain_work_doubles(int T) { return 12 * (int64_t)T * T + 8 * (int64_t)T; }
+extern "C" int64_t hgp_chain_work_doubles(int T) { return PIPE_MATS * (int64_t)T * T + 8 * (int64_t)T + PIPE_FLAG_INTS; }
 extern "C" int64_t hgp_chain_rts_cache_doubles(int T, int n_states) {
     return sl_supported(T) ? (int64_t)n_states * (2 * (int64_t)T * T + T) : 0;
 }
 extern "C" int hgp_chain_small_path(int T) { return sl_supported(T) && !getenv("HGP_CHAIN_V1") ? 1 : 0; }
+
+extern "C" int hgp_chain_pipeline_ctas(void) { return 4; }
+
+extern "C" int hgp_chain_run_ex(const void* descs_device, int n_chains, int T, int pipeline, void* stream) {
+    HGP_REQUIRE(n_chains >= 0 && T > 0 && T <= 1024, "hgp_chain_run_ex: bad sizes");
+    HGP_REQUIRE(pipeline == 0 || pipeline == 1 || pipeline == 4, "hgp_chain_run_ex: pipeline must be 0, 1 or 4");
+    if (pipeline == 0) return hgp_chain_run(descs_device, n_chains, T, stream);
+    if (!sl_supported(T)) { hgp_set_error("hgp_chain_run_ex: the pipelined chain needs the shared-memory path (T = %d)", T); return HGP_E_UNSUPPORTED; }
+    if (n_chains == 0) return 0;
+    const size_t sdyn = sl_dynamic_smem_bytes(T);
+    const hgp_chain_desc* descs = reinterpret_cast<const hgp_chain_desc*>(descs_device);
+    if (pipeline == 1) {
+        cudaError_t e = cudaFuncSetAttribute(chain_kernel_pipe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdyn);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_chain_run_ex: shared memory");
+        chain_kernel_pipe<1><<<n_chains, SL_THREADS, sdyn, (cudaStream_t)stream>>>(descs, T);
+        HGP_LAUNCH_CHECK("hgp_chain_run_ex");
+        return 0;
+    }
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sdyn);
+    if (e != cudaSuccess) return hgp_status(e, "hgp_chain_run_ex: shared memory");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4u * (unsigned)n_chains, 1, 1);
+    cfg.blockDim = dim3(SL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = sdyn;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, chain_kernel_pipe<4>, descs, T);
+    if (e != cudaSuccess) return hgp_status(e, "hgp_chain_run_ex: cluster launch");
+    HGP_LAUNCH_CHECK("hgp_chain_run_ex");
+    return 0;
+}
 
 extern "C" int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream) {
     HGP_REQUIRE(n_chains >= 0 && T > 0 && T <= 1024, "hgp_chain_run: bad sizes");

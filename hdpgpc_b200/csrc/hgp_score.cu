@@ -220,11 +220,34 @@ __device__ __forceinline__ TileItem decode_item(int64_t item, int64_t n_coarse, 
     return r;
 }
 
+// WHITEN = true turns the same pipeline into the table build's  nu_s = W_f mu_s  (hgp_whiten_means_tiles): the "beats" are
+// the rows of the state-mean table, a work item is one (64-state tile, factor f) pair from an explicit list, and the
+// epilogue stores z itself -- transposed back to [state][row] -- for the states of the tile that use factor f, instead
+// of reducing |z - nu|^2.  The reducer warp and the epilogue barriers stay idle.
+struct WhitenArgs {
+    const int2* items;                 // (tile, factor) per work item
+    const int* factor_of_state;        // [S]
+    double* out;                       // [S][T]
+};
+
+template <bool WHITEN>
+__device__ __forceinline__ TileItem tile_item(int64_t item, int64_t n_coarse, int m_splits, int m_per_item, int fine, int M,
+                                              const WhitenArgs& wa) {
+    if (WHITEN) {
+        const int2 w = wa.items[item];
+        TileItem r;
+        r.tile = w.x; r.m_begin = w.y; r.m_end = w.y + 1;
+        return r;
+    }
+    return decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+}
+
+template <bool WHITEN>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ nu,
                    const double* __restrict__ Wpacked, int64_t packed_doubles, const int* __restrict__ state_of,
                    const int* __restrict__ tile_state, const int* __restrict__ factor_of_cluster, int M, int m_per_item,
-                   int m_splits, int64_t n_items, int64_t n_coarse, int fine, double* __restrict__ q) {
+                   int m_splits, int64_t n_items, int64_t n_coarse, int fine, double* __restrict__ q, WhitenArgs wa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nrb = (T + 7) / 8;
     const TileSmem lay = tile_smem_layout(nrb);
@@ -266,10 +289,10 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
             // the ring full across item boundaries, bounded only by the consumers' empty-barrier arrivals.
             if (lane == 0) {
                 for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                    const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+                    const TileItem wi = tile_item<WHITEN>(item, n_coarse, m_splits, m_per_item, fine, M, wa);
                     for (int m = wi.m_begin; m < wi.m_end; ++m) {
-                        const unsigned char* Wp =
-                            reinterpret_cast<const unsigned char*>(Wpacked + (int64_t)factor_of_cluster[m] * packed_doubles);
+                        const unsigned char* Wp = reinterpret_cast<const unsigned char*>(
+                            Wpacked + (int64_t)(WHITEN ? m : factor_of_cluster[m]) * packed_doubles);
                         for (int st = 0; st < n_steps; ++st, ++it) {
                             const int ka = st, kb = nrb - 1 - st;
                             const bool two = kb > ka;
@@ -289,12 +312,12 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
             return;
         }
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+            const TileItem wi = tile_item<WHITEN>(item, n_coarse, m_splits, m_per_item, fine, M, wa);
             const int64_t tile = wi.tile;
             const int m_begin = wi.m_begin, m_end = wi.m_end;
             load_beat_tile(Yfrag, Y, N, T, nrb, tile * BT, warp, lane);
             tile_bar();   // tile complete (every warp but the factor streamer loads it)
-            if (warp == NCW + 1) {
+            if (!WHITEN && warp == NCW + 1) {
                 // Reducer: the consumers never meet at a CTA barrier for the per-beat sum over the eight warps' partial
                 // |z|^2 -- they drop their partials into a double-buffered array, arrive on an mbarrier and move on to
                 // the next cluster; this (otherwise idle, register-donating) warp adds them up in a fixed order and
@@ -326,7 +349,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
         const int rb_of[4] = {warp, 15 - warp, 16 + warp, 31 - warp};
         const int qrow = lane >> 2;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const TileItem wi = decode_item(item, n_coarse, m_splits, m_per_item, fine, M);
+            const TileItem wi = tile_item<WHITEN>(item, n_coarse, m_splits, m_per_item, fine, M, wa);
             const int64_t tile = wi.tile;
             const int m_begin = wi.m_begin, m_end = wi.m_end;
             const int64_t n0 = tile * BT;
@@ -340,7 +363,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                     for (int nt = 0; nt < 8; ++nt) acc[j][nt][0] = acc[j][nt][1] = 0.0;
                 // epilogue operands fetched early so their latency hides under the k-loop:
                 // the tile's uniform state of this cluster (-1: empty cluster, -2: several states) and its nu rows
-                const int st_u = tile_state[tile * M + m];
+                const int st_u = WHITEN ? -1 : tile_state[tile * M + m];
                 double nu_r[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -348,7 +371,7 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                     nu_r[j] = (st_u >= 0 && row < T) ? __ldg(nu + (int64_t)st_u * T + row) : 0.0;
                 }
                 int st_epi = -1;
-                if (st_u == -2 && tid < BT && n0 + tid < N) st_epi = state_of[(n0 + tid) * M + m];   // mixed-state epilogue only
+                if (!WHITEN && st_u == -2 && tid < BT && n0 + tid < N) st_epi = state_of[(n0 + tid) * M + m];   // mixed-state epilogue only
 
                 if (nrb == MAX_NRB) {
                     // T = 256 fast path.  This warp's row blocks are rb_0 = w < rb_1 = 15-w < rb_2 = 16+w < rb_3 = 31-w;
@@ -402,6 +425,24 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[stage]);
                     }
+                }
+                if (WHITEN) {
+                    // ---- table build: nu[state][row] = z for the states of the tile that use this factor ----
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int64_t st = n0 + nt * 8 + 2 * (lane & 3) + e;
+                            if (st < N && wa.factor_of_state[st] == m) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int row = rb_of[j] * 8 + qrow;
+                                    if (row < T) wa.out[st * T + row] = acc[j][nt][e];
+                                }
+                            }
+                        }
+                    }
+                    continue;
                 }
                 // ---- epilogue: z = acc - nu, |z|^2 per beat ----
                 double* rbuf = red + (epi & 1) * (NCW * BT);
@@ -616,9 +657,9 @@ __global__ void tile_uniform_states_kernel(const int* __restrict__ state_of, int
 // nu[s] = W[factor_of_state[s]] mu[s]  (W lower triangular): one CTA per state, one warp per output row.
 __global__ void __launch_bounds__(256)
 whiten_means_kernel(const double* __restrict__ mu, const double* __restrict__ W, const int* __restrict__ factor_of_state,
-                    int T, double* __restrict__ nu) {
+                    const int* __restrict__ state_list, int T, double* __restrict__ nu) {
     extern __shared__ double msm[];
-    const int64_t s = blockIdx.x;
+    const int64_t s = state_list ? state_list[blockIdx.x] : blockIdx.x;
     const double* Wf = W + (int64_t)(factor_of_state ? factor_of_state[s] : s) * T * T;
     for (int t = threadIdx.x; t < T; t += blockDim.x) msm[t] = mu[s * T + t];
     __syncthreads();
@@ -1208,8 +1249,44 @@ extern "C" int hgp_whiten_means(const double* mu, const double* W, const int* fa
     if (factor_of_state && S >= 64 && !getenv("HGP_WHITEN_SCALAR"))
         whiten_tiles_kernel<<<(unsigned)((S + 63) / 64), 256, 0, (cudaStream_t)stream>>>(mu, W, factor_of_state, S, T, nu);
     else
-        whiten_means_kernel<<<(unsigned)S, 256, sizeof(double) * T, (cudaStream_t)stream>>>(mu, W, factor_of_state, T, nu);
+        whiten_means_kernel<<<(unsigned)S, 256, sizeof(double) * T, (cudaStream_t)stream>>>(mu, W, factor_of_state, nullptr, T, nu);
     HGP_LAUNCH_CHECK("hgp_whiten_means");
+    return 0;
+}
+
+// The table build's whitening on the score kernel's own pipeline (T <= 256): `items` lists the (64-state tile, factor)
+// pairs to compute -- every state of tile `x` whose factor is `y` receives nu = W_y mu -- and `state_list` the states
+// left to the row-by-row kernel (tiles with many factors: the duplicated first-member states at the end of a table).
+// Both lists come from the planner on the host side (hdp.LeadTables) and depend on factor_of_state only.
+extern "C" int hgp_whiten_means_tiles(const double* mu, const double* W, const double* Wpacked, const int* factor_of_state,
+                                      int64_t S, int T, const int* items, int64_t n_items, const int* state_list,
+                                      int64_t n_list, double* nu, void* stream) {
+    HGP_REQUIRE(S >= 0 && T > 0 && n_items >= 0 && n_list >= 0, "hgp_whiten_means_tiles: bad sizes");
+    HGP_REQUIRE(factor_of_state != nullptr, "hgp_whiten_means_tiles: factor_of_state required");
+    if (T > 256) { hgp_set_error("hgp_whiten_means_tiles: need T <= 256 (got %d)", T); return HGP_E_UNSUPPORTED; }
+    if (n_items > 0) {
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (n_sm <= 0) n_sm = 148;
+        }
+        const int nrb = (T + 7) / 8;
+        const TileSmem lay = tile_smem_layout(nrb);
+        cudaError_t e = cudaFuncSetAttribute(score_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_whiten_means_tiles: smem attribute");
+        const int grid = (int)hgp_min64(n_items, n_sm);
+        score_tiles_kernel<true><<<grid, TILE_THREADS, lay.total, (cudaStream_t)stream>>>(
+            mu, S, T, nullptr, Wpacked, hgp_packed_factor_bytes(T) / 8, nullptr, nullptr, nullptr, 0, 1, 1, n_items, n_items, 1,
+            nullptr, WhitenArgs{reinterpret_cast<const int2*>(items), factor_of_state, nu});
+        HGP_LAUNCH_CHECK("hgp_whiten_means_tiles");
+    }
+    if (n_list > 0) {
+        whiten_means_kernel<<<(unsigned)n_list, 256, sizeof(double) * T, (cudaStream_t)stream>>>(mu, W, factor_of_state,
+                                                                                              state_list, T, nu);
+        HGP_LAUNCH_CHECK("hgp_whiten_means_tiles: listed states");
+    }
     return 0;
 }
 
@@ -1229,7 +1306,7 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
     }
     const int nrb = (T + 7) / 8;
     const TileSmem lay = tile_smem_layout(nrb);
-    cudaError_t e = cudaFuncSetAttribute(score_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+    cudaError_t e = cudaFuncSetAttribute(score_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
     if (e != cudaSuccess) return hgp_status(e, "hgp_score_tiles: smem attribute");
     const int64_t n_tiles = (N + BT - 1) / BT;
     // split the cluster range so that the item count is >= ~24 waves of the persistent grid (tail < 4 %)
@@ -1248,9 +1325,9 @@ extern "C" int hgp_score_tiles(const double* Y, int64_t N, int T, const double* 
         n_coarse = n_all - rem;
     }
     const int64_t n_items = n_coarse + (n_all - n_coarse) * fine;
-    score_tiles_kernel<<<grid, TILE_THREADS, lay.total, (cudaStream_t)stream>>>(
+    score_tiles_kernel<false><<<grid, TILE_THREADS, lay.total, (cudaStream_t)stream>>>(
         Y, N, T, nu, Wpacked, hgp_packed_factor_bytes(T) / 8, state_of, tile_state, factor_of_cluster, M, m_per_item,
-        m_splits, n_items, n_coarse, fine, q);
+        m_splits, n_items, n_coarse, fine, q, WhitenArgs{nullptr, nullptr, nullptr});
     HGP_LAUNCH_CHECK("hgp_score_tiles");
     if (snr) return hgp_snr_states(Y, N, T, mu_sm, snr_state_of, M, snr, stream);
     return 0;

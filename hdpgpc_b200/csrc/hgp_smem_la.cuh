@@ -11,6 +11,9 @@
 //     sweep, so that X = M^{-1} B is two triangular tensor-core products instead of two latency-bound substitutions.
 // Used by the chain kernel (hgp_chain.cu, chain_kernel_small) and the hyper-parameter fit.
 //
+// Global operands are read with ld.global.cg (L2 only): the pipelined chain kernel hands matrices and vectors from one CTA
+// of a cluster to another through global memory, and a line left in a reader's L1 by an earlier step would be stale.
+//
 // All buffer accesses go through `sl_dyn`, the kernel's dynamic shared memory, so that they compile to LDS / STS (a
 // pointer fetched from a struct would be a generic pointer: LD.E + address translation in the inner loops).
 #pragma once
@@ -103,7 +106,7 @@ __device__ __forceinline__ void sl_load(SlCtx& c, int b, const double* __restric
         for (int i0 = threadIdx.x; i0 < n2; i0 += SL_THREADS * U) {
             double2 v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n2) v[u] = __ldg(g2 + i); }
+            for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n2) v[u] = __ldcg(g2 + i); }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = i0 + u * SL_THREADS;
@@ -116,7 +119,7 @@ __device__ __forceinline__ void sl_load(SlCtx& c, int b, const double* __restric
         for (int i0 = threadIdx.x; i0 < n; i0 += SL_THREADS * U) {
             double v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) v[u] = __ldg(g + i); }
+            for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) v[u] = __ldcg(g + i); }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = i0 + u * SL_THREADS;
@@ -150,14 +153,14 @@ __device__ __forceinline__ void sl_gemv(double* __restrict__ y, const double* __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double xv[3], acc[12];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { const int k = lane + 32 * q; xv[q] = (k < T) ? x[k] : 0.0; }
+    for (int q = 0; q < 3; ++q) { const int k = lane + 32 * q; xv[q] = (k < T) ? __ldcg(x + k) : 0.0; }
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
         const int r = warp + 8 * i;
         double a = 0.0;
         if (r < T) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { const int k = lane + 32 * q; if (k < T) a += __ldg(A + (int64_t)r * T + k) * xv[q]; }
+            for (int q = 0; q < 3; ++q) { const int k = lane + 32 * q; if (k < T) a += __ldcg(A + (int64_t)r * T + k) * xv[q]; }
         }
         acc[i] = a;
     }
@@ -168,7 +171,7 @@ __device__ __forceinline__ void sl_gemv(double* __restrict__ y, const double* __
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
         const int r = warp + 8 * i;
-        if (r < T && lane == 0) y[r] = alpha * acc[i] + (y0 ? beta * y0[r] : 0.0);
+        if (r < T && lane == 0) y[r] = alpha * acc[i] + (y0 ? beta * __ldcg(y0 + r) : 0.0);
     }
     __syncthreads();
 }
@@ -179,7 +182,7 @@ __device__ __forceinline__ void sl_axpby(double* __restrict__ D, double a, const
     for (int i0 = threadIdx.x; i0 < n; i0 += SL_THREADS * U) {
         double xv[U], yv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) { xv[u] = X[i]; yv[u] = Y[i]; } }
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) { xv[u] = __ldcg(X + i); yv[u] = __ldcg(Y + i); } }
 #pragma unroll
         for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) D[i] = a * xv[u] + b * yv[u]; }
     }
@@ -190,7 +193,7 @@ __device__ __forceinline__ void sl_copy(double* __restrict__ D, const double* __
     for (int i0 = threadIdx.x; i0 < n; i0 += SL_THREADS * U) {
         double v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) v[u] = S[i]; }
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) v[u] = __ldcg(S + i); }
 #pragma unroll
         for (int u = 0; u < U; ++u) { const int i = i0 + u * SL_THREADS; if (i < n) D[i] = v[u]; }
     }
@@ -286,7 +289,7 @@ static __device__ __noinline__ void sl_gemm(SlCtx& c, double* Cg, const double* 
             if (i >= mcnt) continue;
             const int r = r0 + 8 * i + lr;
             if (r >= T) continue;
-            const double ur = (ep.u ? ep.s * ep.u[r] : 0.0);
+            const double ur = (ep.u ? ep.s * __ldcg(ep.u + r) : 0.0);
             double2 dv[SL_NT];
             if (ep.D) {
 #pragma unroll
@@ -294,8 +297,8 @@ static __device__ __noinline__ void sl_gemm(SlCtx& c, double* Cg, const double* 
                     const int cc = c0 + 8 * j + 2 * lk;
                     dv[j] = make_double2(0.0, 0.0);
                     if (j < ncnt && cc < T) {
-                        if (pair_ok) dv[j] = *reinterpret_cast<const double2*>(ep.D + (int64_t)r * T + cc);
-                        else { dv[j].x = ep.D[(int64_t)r * T + cc]; if (cc + 1 < T) dv[j].y = ep.D[(int64_t)r * T + cc + 1]; }
+                        if (pair_ok) dv[j] = __ldcg(reinterpret_cast<const double2*>(ep.D + (int64_t)r * T + cc));
+                        else { dv[j].x = __ldcg(ep.D + (int64_t)r * T + cc); if (cc + 1 < T) dv[j].y = __ldcg(ep.D + (int64_t)r * T + cc + 1); }
                     }
                 }
             }
@@ -310,7 +313,7 @@ static __device__ __noinline__ void sl_gemm(SlCtx& c, double* Cg, const double* 
                 if (ep.D) { v.x += ep.beta * dv[j].x; v.y += ep.beta * dv[j].y; }
                 if (cc == r) v.x += ep.diag_add;
                 if (cc + 1 == r) v.y += ep.diag_add;
-                if (ep.u) { v.x += ur * ep.v[cc]; if (cc + 1 < T) v.y += ur * ep.v[cc + 1]; }
+                if (ep.u) { v.x += ur * __ldcg(ep.v + cc); if (cc + 1 < T) v.y += ur * __ldcg(ep.v + cc + 1); }
                 if (pair_ok) {                       // T even: cc + 1 < T, 16-byte aligned everywhere (LD is even as well)
                     *reinterpret_cast<double2*>(Cs + r * LD + cc) = v;
                     *reinterpret_cast<double2*>(Cg + (int64_t)r * T + cc) = v;

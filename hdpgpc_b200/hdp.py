@@ -91,6 +91,7 @@ class LeadTables:
         self.tile_state = None                      # [ceil(N / 64), M] uniform state per (tile, cluster) or -2
         self.factor_of_cluster = None
         self.pair_n = self.pair_m = None
+        self._whiten_plan = None
         self.use_tiles = False
         self.block_path = T > 256                   # beats longer than the tile kernel's 256 rows: hgp_score_blocks
         if tile_path is None:
@@ -111,9 +112,8 @@ class LeadTables:
             return  # mostly per-state covariances (estimation_limit=None regime): pair kernel for everything
         self.use_tiles = True
         self.factor_of_cluster = main_c.to(I32).contiguous()
-        self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
+        self._whiten()
         if not self.block_path:
-            self.Wpacked = ops.pack_factors(self.W)
             self.tile_state = ops.tile_uniform_states(self.state_of)
         if n_exc:
             nz = torch.nonzero(exc)
@@ -135,10 +135,22 @@ class LeadTables:
         if mu_sm is not None:
             self.mu_sm = mu_sm
         if self.use_tiles:
-            self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
-            if not self.block_path:
-                self.Wpacked = ops.pack_factors(self.W)
+            self._whiten()
         return info
+
+    def _whiten(self):
+        """Packed factors and whitened state means nu = W_f mu.  Tables of at least a few tiles go through the tile
+        kernel's own pipeline (ops.whiten_means_tiles; the work lists depend on factor_of_state only and are kept)."""
+        if self.block_path:
+            self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
+            return
+        self.Wpacked = ops.pack_factors(self.W)
+        if self.mu.shape[0] < 4 * ops.tile_beats():
+            self.nu = ops.whiten_means(self.mu, self.W, self.factor_of_state)
+            return
+        if self._whiten_plan is None:
+            self._whiten_plan = ops.whiten_plan(self.factor_of_state)
+        self.nu = ops.whiten_means_tiles(self.mu, self.W, self.Wpacked, self.factor_of_state, self._whiten_plan)
 
     def score(self, out, snr_out=None):
         """q (and, when snr_out is given, the SNR statistic) for this lead plane."""

@@ -1,6 +1,7 @@
 """Thin Python wrappers over the C ABI (include/hdpgpc_b200.h).  Tensors are torch CUDA tensors
 (device memory + streams are torch's; the arithmetic is the library's).  No CPU fallback."""
 import ctypes
+import os
 
 import torch
 
@@ -122,6 +123,46 @@ def whiten_means(mu, W, factor_of_state=None):
     if factor_of_state is not None:
         factor_of_state = _dev(factor_of_state).to(I32).contiguous()
     check(lib.hgp_whiten_means(ptr(mu), ptr(W), ptr(factor_of_state), S, T, ptr(nu), stream_ptr()), "hgp_whiten_means")
+    return nu
+
+
+def whiten_plan(factor_of_state, max_factors_per_tile=4):
+    """Work lists of hgp_whiten_means_tiles for a state table (they depend on factor_of_state only, so a table build on
+    unchanged index maps re-uses them): the (tile, factor) pairs of the 64-state tiles that mix at most
+    `max_factors_per_tile` factors, and the states of all other tiles.  Returns (items [n, 2] int32, state_list int32)."""
+    lib = _lib_ready()
+    fos = _dev(factor_of_state).to(torch.int64).contiguous()
+    S = fos.numel()
+    bt = int(lib.hgp_tile_beats())
+    n_tiles = (S + bt - 1) // bt
+    pad = torch.full((n_tiles * bt,), -1, dtype=torch.int64, device=fos.device)
+    pad[:S] = fos
+    pad = pad.view(n_tiles, bt)
+    srt = torch.sort(pad, dim=1).values
+    new = torch.ones_like(srt, dtype=torch.bool)
+    new[:, 1:] = srt[:, 1:] != srt[:, :-1]
+    new &= srt >= 0
+    fast = new.sum(dim=1) <= max_factors_per_tile                       # [n_tiles]
+    sel = new & fast[:, None]
+    tiles = torch.arange(n_tiles, device=fos.device)[:, None].expand_as(srt)
+    items = torch.stack([tiles[sel], srt[sel]], dim=1).to(I32).contiguous()
+    slow_states = torch.nonzero(~fast[torch.arange(S, device=fos.device) // bt]).reshape(-1).to(I32).contiguous()
+    return items, slow_states
+
+
+def whiten_means_tiles(mu, W, Wpacked, factor_of_state, plan):
+    """nu = whiten_means(mu, W, factor_of_state) computed on the tile kernel's pipeline (see hgp_whiten_means_tiles)."""
+    lib = _lib_ready()
+    mu = _dev(mu).contiguous()
+    S, T = mu.shape
+    items, slow = plan
+    W = _dev(W).contiguous()
+    factor_of_state = _dev(factor_of_state).to(I32).contiguous()
+    nu = torch.empty_like(mu)
+    check(lib.hgp_whiten_means_tiles(ptr(mu), ptr(W), ptr(Wpacked), ptr(factor_of_state), S, T,
+                                     ptr(items) if items.numel() else None, items.shape[0],
+                                     ptr(slow) if slow.numel() else None, slow.numel(), ptr(nu), stream_ptr()),
+          "hgp_whiten_means_tiles")
     return nu
 
 
@@ -318,11 +359,22 @@ def pred_dist_inducing(x_basis, x_post, mu, mu_idx, Sigma, sig_idx, kernel):
     return f, cov, info
 
 
-def chain_run(descs, T):
-    """descs: list of dicts with the fields of hgp_chain_desc (tensors or scalars).  Runs all chains in one launch."""
+def chain_run(descs, T, pipeline=None):
+    """descs: list of dicts with the fields of hgp_chain_desc (tensors or scalars).  Runs all chains in one launch.
+    pipeline: None = choose (a four-CTA cluster per chain when the chains are few, long and replay whole member steps on
+    the shared-memory path; one CTA per chain otherwise), 0 / 1 / 4 = force (see hgp_chain_run_ex)."""
     import ctypes as _ct
     lib = _lib_ready()
     n = len(descs)
+    if pipeline is None:
+        pipeline = 0
+        eligible = (n > 0 and int(lib.hgp_chain_small_path(T)) and all(int(d.get("phases", 0)) in (0, 7, 15) for d in descs))
+        forced = os.environ.get("HGP_CHAIN_PIPELINE")          # tests / A-B timing: 0, 1 or 4 wherever the mode applies
+        if forced is not None:
+            pipeline = int(forced) if eligible else 0
+        elif (eligible and min(int(d["n_members"]) for d in descs) >= 4
+              and n * int(lib.hgp_chain_pipeline_ctas()) <= torch.cuda.get_device_properties(0).multi_processor_count):
+            pipeline = int(lib.hgp_chain_pipeline_ctas())
     arr = (_lib.ChainDesc * n)()
     keep = []
     for i, d in enumerate(descs):
@@ -334,7 +386,7 @@ def chain_run(descs, T):
             setattr(arr[i], name, v)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     dev = host.cuda()
-    check(lib.hgp_chain_run(ptr(dev), n, T, stream_ptr()), "hgp_chain_run")
+    check(lib.hgp_chain_run_ex(ptr(dev), n, T, int(pipeline), stream_ptr()), "hgp_chain_run_ex")
     torch.cuda.current_stream().synchronize()
     return keep
 

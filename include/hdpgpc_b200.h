@@ -92,6 +92,13 @@ int hgp_tile_uniform_states(const int* state_of, int64_t N, int M, int* tile_sta
 /* nu[s] = W[factor_of_state[s]] mu[s] for s in [0, S)  (factor_of_state NULL: factor s). */
 int hgp_whiten_means(const double* mu, const double* W, const int* factor_of_state, int64_t S, int T, double* nu,
                      void* stream);
+/* The same product for a whole table build on the tile kernel's tensor-core pipeline (T <= 256, Wpacked from
+ * hgp_pack_factors): items = n_items (tile, factor) int pairs -- every state s in [64 tile, 64 tile + 64) with
+ * factor_of_state[s] == factor receives nu[s] = W_factor mu[s]; state_list = n_list states computed row by row from the
+ * plain factors W instead (tiles that mix many factors).  A state must be covered by exactly one of the two lists. */
+int hgp_whiten_means_tiles(const double* mu, const double* W, const double* Wpacked, const int* factor_of_state,
+                           int64_t S, int T, const int* items, int64_t n_items, const int* state_list, int64_t n_list,
+                           double* nu, void* stream);
 int hgp_score_tiles(const double* Y, int64_t N, int T, const double* nu, const double* Wpacked,
                     const int* state_of, const int* tile_state, const int* factor_of_cluster, int M, double* q,
                     const double* mu_sm, const int* snr_state_of, double* snr, void* stream);
@@ -227,6 +234,13 @@ int64_t hgp_chain_work_doubles(int T);
 int64_t hgp_chain_rts_cache_doubles(int T, int n_states);   /* 0 when T is outside the shared-memory path */
 int hgp_chain_small_path(int T);                            /* 1: hgp_chain_run uses the shared-memory kernel for this T */
 int hgp_chain_run(const void* descs_device, int n_chains, int T, void* stream);
+/* The same replay with the member step of every chain spread over a thread-block cluster: pipeline = 4 gives each chain
+ * four CTAs (Kalman update | pair-smoother gain | MNIW over (A, Gamma) | MNIW over (C, Sigma), see hgp_chain.cu) -- for the
+ * few long chains of a real fit, 4 n_chains <= SM count; pipeline = 1 runs the same re-organised step in one CTA;
+ * pipeline = 0 is hgp_chain_run.  Shared-memory path only (hgp_chain_small_path(T)), whole member steps only (phases 0, 7
+ * or 15 in every descriptor; status[0] = -2 otherwise). */
+int hgp_chain_pipeline_ctas(void);
+int hgp_chain_run_ex(const void* descs_device, int n_chains, int T, int pipeline, void* stream);
 /* Unit-test hook for the CTA-level routines the chain kernel is built from (gemm variants, chol, trsm, LU solve). */
 int hgp_la_op(int op, double* A, double* B, double* C, int* piv, int T, int* info, void* stream);
 

@@ -218,12 +218,15 @@ def test_shared_memory_linear_algebra(T):
     assert ops.la_op(14, cu(bad), aux, Li) == 1
 
 
+@pytest.mark.parametrize("pipeline", ["0", "1", "4"])
 @pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2", "offline_rec100_T90_L1",
                                   "offline_rec100_T30_L1_lim30"])
-def test_chain_replay_vs_reference(golden, name):
+def test_chain_replay_vs_reference(golden, name, pipeline, monkeypatch):
     """full_pass_weighted on the device (Kalman + pair smoother + MNIW per member, full RTS pass) against the
-    reference's golden chain dumps: per-step states and the (q, q_lat) it returns."""
+    reference's golden chain dumps: per-step states and the (q, q_lat) it returns.  pipeline: one CTA per chain (0), the
+    re-organised member step in one CTA (1), a four-CTA cluster per chain (4, hgp_chain_run_ex)."""
     import hdpgpc_b200 as hb
+    monkeypatch.setenv("HGP_CHAIN_PIPELINE", pipeline)
     z = golden(name)
     Y = z["data"]
     full = "chain_0_Sigma" in z.files
@@ -251,7 +254,8 @@ def test_chain_replay_vs_reference(golden, name):
                 assert np.max(np.abs(mine[-1] - ref)) < 1e-8 * np.max(np.abs(ref))
 
 
-def test_batch_chain_keeps_parameters_on_mniw_failure(golden, capsys):
+@pytest.mark.parametrize("pipeline", [0, 1, 4])
+def test_batch_chain_keeps_parameters_on_mniw_failure(golden, capsys, pipeline):
     """A Cholesky failure inside the MNIW update must not abort the chain: the reference catches the LinAlgError, prints
     and keeps the previous posteriors of BOTH distributions for that member (GPI_model.py:1068-1071).  Forced here with a
     non-SPD row covariance in the observation prior (every update fails, so the parameter sets that get appended are
@@ -271,7 +275,7 @@ def test_batch_chain_keeps_parameters_on_mniw_failure(golden, capsys):
                             free_deg=float(z["free_deg_MNIV"]))
     d = gp._chain_prepare(cu(Y), cu(resp))
     d["obs_m_r_cov"].copy_(-torch.eye(T, dtype=torch.float64, device="cuda"))
-    ops.chain_run([d], T)
+    ops.chain_run([d], T, pipeline=pipeline)
     gp._chain_finish(d)
     assert gp.mniw_first_failed_member == 1                  # the first update happens at the second member
     assert "Alg error matrix ill conditioned." in capsys.readouterr().out
@@ -1043,6 +1047,21 @@ def test_table_build_kernels(T, S):
     nu = ops.whiten_means(cu(mu), W, cu(fos).to(torch.int32)).cpu().numpy()
     ref = np.einsum("srk,sk->sr", W.cpu().numpy()[fos], mu)
     assert np.max(np.abs(nu - ref)) < 1e-12 * np.max(np.abs(ref))
+    # the same table through the score kernel's own pipeline (hgp_whiten_means_tiles): a duplicated-first-member tail of
+    # one factor per state (row-by-row list), tiles with one to three factors (work items), a ragged last tile
+    fos2 = np.concatenate([fos, np.arange(70, dtype=np.int32) % F]).astype(np.int32)
+    mu2 = np.concatenate([mu, rng.standard_normal((70, T)) * 50.0])
+    plan = ops.whiten_plan(cu(fos2).to(torch.int32))
+    items, slow = plan[0].cpu().numpy(), plan[1].cpu().numpy()
+    covered = np.zeros(S + 70, dtype=np.int64)
+    for t, f in items:
+        covered[64 * t:64 * t + 64] += fos2[64 * t:64 * t + 64] == f
+    covered[slow] += 1
+    assert np.all(covered == 1) and len(slow) >= 64 and (S < 256 or len(items) >= S // 64)
+    Wp = ops.pack_factors(W)
+    nu2 = ops.whiten_means_tiles(cu(mu2), W, Wp, cu(fos2).to(torch.int32), plan).cpu().numpy()
+    ref2 = np.einsum("srk,sk->sr", W.cpu().numpy()[fos2], mu2)
+    assert np.max(np.abs(nu2 - ref2)) < 1e-12 * np.max(np.abs(ref2))
 
 
 @pytest.mark.parametrize("M", [40, 100])

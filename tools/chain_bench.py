@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Secondary measurements (reported beside the headline): chain replay in member-steps/s and
 q_lat in members/s at T=256, next to the CPU oracle on the same chain.
-usage: python tools/chain_bench.py [n_chains] [members_per_chain] [T]"""
+usage: [HGP_CHAIN_PIPELINE=0|1|4] python tools/chain_bench.py [n_chains] [members_per_chain] [T] [nocpu]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -53,6 +53,10 @@ e0.record()
 for gp in gp_list: gp.compute_q_lat_all(Y[0])
 e1.record(); torch.cuda.synchronize()
 res["qlat_ms"] = e0.elapsed_time(e1); res["qlat_members_per_s"] = steps / (res["qlat_ms"] * 1e-3)
+res["pipeline"] = os.environ.get("HGP_CHAIN_PIPELINE", "auto")
+if len(sys.argv) > 4 and sys.argv[4] == "nocpu":
+    print(json.dumps(res))
+    sys.exit(0)
 # CPU oracle on one chain of the same data
 from oracle import hdpgpc_oracle as O
 torch.set_num_threads(os.cpu_count())
