@@ -235,6 +235,184 @@ hmm_scan_kernel(const double* __restrict__ e, int64_t N, int K, const double* __
 }
 
 // ------------------------------------------------------------------------------------------
+// The same scan for many states (K > 32): EIGHT chunks per CTA on the FP64 tensor cores.
+// One step of one chunk is a K x K matrix-vector product -- 16K multiply-adds behind one another's shuffles and two CTA
+// barriers; at K = 128 the one-chunk kernel holds its rows in 98 registers x 512 threads (one CTA per SM) and took 2300
+// cycles per step, 9x the FP64 pipe's time for the arithmetic (cfg5: 2 x 16.4 ms per sweep).  Eight chunks side by
+// side turn the step into a K x K x 8 product: the transition operand stays in registers as DMMA A fragments (warp w
+// owns rows 8w .. 8w+7, K/4 fragments per lane), the eight previous messages are the B operand in shared memory, and
+// lane (lr, lk) of warp w ends up with row 8w+lr of chunks 2lk and 2lk+1 -- the barriers, the normalisation and the
+// message stores are paid once per eight chunk-steps.  The arithmetic of a step (four DMMA accumulation chains added in a
+// fixed order, sums over warps in warp order) depends on nothing but the incoming message, so the fixed-point argument
+// of the chunk protocol holds unchanged; which kernel runs depends on K only, never on N, so a sharded scan stays
+// bitwise equal to the unsharded one.
+template <int KP, bool BACKWARD>
+__global__ void __launch_bounds__(4 * KP)
+hmm_scan8_kernel(const double* __restrict__ e, int64_t N, int K, const double* __restrict__ pi,
+                 const double* __restrict__ Mat, const double* __restrict__ boundary, int has_boundary,
+                 double* __restrict__ msgs, double* __restrict__ marg, const double* __restrict__ ends_in,
+                 double* __restrict__ ends_out, int* __restrict__ changed, int repair, int rebase) {
+    constexpr int NWARP = KP / 8;
+    constexpr int LDP = KP + 4;                       // == 4 (mod 8): the B-fragment loads of a half-warp hit 16 banks
+    constexpr int NKS = KP / 4;
+    __shared__ __align__(16) double s_prev[8 * LDP];  // forward: alpha_{t-1};  backward: u_{t+1} = beta_{t+1} * e_{t+1}
+    __shared__ __align__(16) double s_wsum[NWARP * 8];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int row = 8 * warp + lr;
+    const int64_t C = (N + CHUNK - 1) / CHUNK;
+    const int64_t cbase = (int64_t)blockIdx.x * 8;
+
+    double a[NKS];
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+        const int col = 4 * ks + lk;
+        a[ks] = (row < K && col < K) ? Mat[(int64_t)row * K + col] : 0.0;
+    }
+
+    // ---- the eight chunks: starting messages (all threads) and this lane's two chunks ----
+    int maxlen = 0;
+    for (int n = 0; n < 8; ++n) {
+        const int64_t c = cbase + n;
+        if (c >= C) break;
+        const bool exact = BACKWARD ? (c == C - 1) : (c == 0);
+        if (repair && exact && !rebase) continue;                        // nothing to repair: ends copied below
+        const int64_t t0 = c * CHUNK, t1 = hgp_min64(N, t0 + CHUNK);
+        maxlen = max(maxlen, (int)(t1 - t0));
+    }
+    for (int idx = tid; idx < 8 * KP; idx += 4 * KP) {
+        const int n = idx / KP, k = idx - n * KP;
+        const int64_t c = cbase + n;
+        double v = 0.0;
+        if (c < C && k < K) {
+            const bool exact = BACKWARD ? (c == C - 1) : (c == 0);
+            const int64_t t1 = hgp_min64(N, c * CHUNK + CHUNK);
+            if (!BACKWARD) {
+                if (exact) v = has_boundary ? boundary[k] : pi[k];
+                else if (repair) v = ends_in[(c - 1) * K + k];
+                else v = 1.0 / (double)K;                                 // guess
+            } else {
+                if (exact) v = has_boundary ? boundary[k] : 0.0;
+                else if (repair) v = ends_in[(c + 1) * K + k];
+                else v = e[t1 * K + k];                                   // guess beta_{t1} = 1  ->  u = e_{t1}
+            }
+        }
+        s_prev[n * LDP + k] = v;
+    }
+    int len[2];
+    int64_t tcur[2];
+    bool first_plain[2];        // the very first beat of the global sequence: no matrix product (GPI_HDP.py:3598, :3642)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int64_t c = cbase + 2 * lk + j;
+        len[j] = 0; tcur[j] = 0; first_plain[j] = false;
+        if (c < C) {
+            const bool exact = BACKWARD ? (c == C - 1) : (c == 0);
+            const int64_t t0 = c * CHUNK, t1 = hgp_min64(N, t0 + CHUNK);
+            if (!(repair && exact && !rebase)) len[j] = (int)(t1 - t0);
+            tcur[j] = BACKWARD ? t1 - 1 : t0;
+            first_plain[j] = exact && !has_boundary;
+        }
+    }
+    const int64_t tstep = BACKWARD ? -1 : 1;
+    __syncthreads();
+
+    double e_next[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) e_next[j] = (len[j] > 0 && row < K) ? e[tcur[j] * K + row] : 0.0;
+
+    int stop_step = maxlen;      // repair: the step at which every chunk still running reproduced its stored message
+    for (int step = 0; step < maxlen; ++step) {
+        double e_t[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            e_t[j] = e_next[j];
+            if (step + 1 < len[j] && row < K) e_next[j] = e[(tcur[j] + tstep) * K + row];
+        }
+        // ---- (transition operand) x (eight previous messages): four accumulation chains, added in a fixed order ----
+        double acc[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+        const double* bp = s_prev + lr * LDP + lk;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) dmma884(acc[ks & 3][0], acc[ks & 3][1], a[ks], bp[4 * ks]);
+        double v[2], contrib[2];
+        bool plain[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double d = (acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]);
+            plain[j] = first_plain[j] && step == 0;
+            if (plain[j]) v[j] = BACKWARD ? 1.0 : s_prev[(2 * lk + j) * LDP + (row < KP ? row : 0)] * e_t[j];
+            else v[j] = BACKWARD ? d : d * e_t[j];
+            if (row >= K || step >= len[j]) v[j] = 0.0;
+            // forward: sum over all states (:3601); backward: all but the last state (:3646)
+            contrib[j] = (row < (BACKWARD ? K - 1 : K)) ? v[j] : 0.0;
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            contrib[0] += __shfl_xor_sync(0xffffffffu, contrib[0], o);
+            contrib[1] += __shfl_xor_sync(0xffffffffu, contrib[1], o);
+        }
+        if (lr == 0) *reinterpret_cast<double2*>(&s_wsum[warp * 8 + 2 * lk]) = make_double2(contrib[0], contrib[1]);
+        __syncthreads();          // partial sums complete; every warp has read s_prev
+        double tot[2] = {0.0, 0.0};
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) {
+            const double2 p2 = *reinterpret_cast<const double2*>(&s_wsum[w * 8 + 2 * lk]);
+            tot[0] += p2.x;
+            tot[1] += p2.y;
+        }
+        int same = 1;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (step < len[j]) {
+                if (BACKWARD && plain[j]) tot[j] = 1.0;
+                else v[j] = v[j] * (1.0 / tot[j]);       // reciprocal + multiply: see the one-chunk kernel
+                if (row < K) {
+                    const int64_t t = tcur[j];
+                    if (repair) {
+                        const double old = msgs[t * K + row];
+                        if (__double_as_longlong(old) != __double_as_longlong(v[j])) { same = 0; msgs[t * K + row] = v[j]; }
+                    } else {
+                        msgs[t * K + row] = v[j];
+                    }
+                    s_prev[(2 * lk + j) * LDP + row] = BACKWARD ? v[j] * e_t[j] : v[j];
+                    if (!BACKWARD && marg && row == 0) marg[t] = tot[j];     // margPrObs[t] of forward() (:3601)
+                }
+                tcur[j] += tstep;
+            }
+        }
+        if (repair) {
+            if (__syncthreads_and(same)) { stop_step = step; break; }
+        } else {
+            __syncthreads();
+        }
+    }
+
+    // ---- boundary messages handed to the neighbour chunks ----
+    for (int idx = tid; idx < 8 * KP; idx += 4 * KP) {
+        const int n = idx / KP, k = idx - n * KP;
+        const int64_t c = cbase + n;
+        if (c >= C || k >= K) continue;
+        const bool exact = BACKWARD ? (c == C - 1) : (c == 0);
+        const int len_n = (int)(hgp_min64(N, c * CHUNK + CHUNK) - c * CHUNK);
+        // a chunk that was still running when the loop stopped has a stored tail that is already exact; a (shorter) chunk
+        // that had run to its end before that hands over the message it ended with
+        if (repair && ((exact && !rebase) || stop_step < len_n)) {
+            ends_out[c * K + k] = ends_in[c * K + k];
+        } else {
+            const double out = s_prev[n * LDP + k];
+            if (repair) {
+                const double old = ends_in[c * K + k];
+                if (__double_as_longlong(old) != __double_as_longlong(out)) atomicOr(changed, 1);
+            }
+            ends_out[c * K + k] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // hard responsibilities: one warp per beat
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -361,13 +539,27 @@ static HmmSide* hmm_side() {
     return &side;
 }
 
+// forward / backward scan launch: the eight-chunk tensor-core kernel for KP >= 64, one chunk per CTA below
+template <int KP, bool BACKWARD>
+static void launch_scan(const double* e, int64_t N, int K, const double* pi, const double* Mat, const double* boundary,
+                        int has_boundary, double* msgs, double* marg, const double* ends_in, double* ends_out, int* changed,
+                        int repair, int rebase, cudaStream_t st) {
+    const int64_t C = (N + CHUNK - 1) / CHUNK;
+    if (KP >= 64) {
+        hmm_scan8_kernel<(KP >= 64 ? KP : 64), BACKWARD><<<(unsigned)((C + 7) / 8), 4 * KP, 0, st>>>(
+            e, N, K, pi, Mat, boundary, has_boundary, msgs, marg, ends_in, ends_out, changed, repair, rebase);
+    } else {
+        hmm_scan_kernel<KP, BACKWARD><<<(unsigned)C, 4 * KP, 0, st>>>(e, N, K, pi, Mat, boundary, has_boundary, msgs, marg,
+                                                                       ends_in, ends_out, changed, repair, rebase);
+    }
+}
+
 template <int KP>
 int launch_scans(const double* e, int64_t N, int K, const double* pi, const double* PiT, const double* Pi,
                  const double* boundary_in, int has_prev, int has_next, double* alpha, double* beta, double* marg,
                  double* endsA, double* endsB, int* changed, int* changed_host, int* rounds_host, cudaStream_t st,
                  int warm) {
     const int64_t C = (N + CHUNK - 1) / CHUNK;
-    const int threads = 4 * KP;
     double* fa[2] = {endsA, endsA + C * K};
     double* fb[2] = {endsB, endsB + C * K};
     HmmSide* side = hmm_side();
@@ -377,11 +569,10 @@ int launch_scans(const double* e, int64_t N, int K, const double* pi, const doub
     if (!warm) {
     cudaEventRecord(side->fork, st);
     cudaStreamWaitEvent(sb, side->fork, 0);
-    hmm_scan_kernel<KP, false><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, PiT, boundary_in, has_prev, alpha,
-                                                                 marg, nullptr, fa[0], changed, 0, 0);
+    launch_scan<KP, false>(e, N, K, pi, PiT, boundary_in, has_prev, alpha, marg, nullptr, fa[0], changed, 0, 0, st);
     HGP_LAUNCH_CHECK("hmm forward scan");
-    hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, sb>>>(e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr,
-                                                                has_next, beta, nullptr, nullptr, fb[0], changed + 1, 0, 0);
+    launch_scan<KP, true>(e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr, has_next, beta, nullptr, nullptr, fb[0],
+                          changed + 1, 0, 0, sb);
     HGP_LAUNCH_CHECK("hmm backward scan");
     cudaEventRecord(side->join, sb);
     cudaStreamWaitEvent(st, side->join, 0);
@@ -398,14 +589,13 @@ int launch_scans(const double* e, int64_t N, int K, const double* pi, const doub
                 cudaStreamWaitEvent(sb, side->fork, 0);
             }
             if (need_f) {
-                hmm_scan_kernel<KP, false><<<(unsigned)C, threads, 0, st>>>(e, N, K, pi, PiT, boundary_in, has_prev,
-                                                                             alpha, marg, fa[cur], fa[cur ^ 1], changed, 1, first_rebase);
+                launch_scan<KP, false>(e, N, K, pi, PiT, boundary_in, has_prev, alpha, marg, fa[cur], fa[cur ^ 1], changed, 1,
+                                       first_rebase, st);
                 HGP_LAUNCH_CHECK("hmm forward repair");
             }
             if (need_b) {
-                hmm_scan_kernel<KP, true><<<(unsigned)C, threads, 0, sb>>>(
-                    e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr, has_next, beta, nullptr, fb[cur], fb[cur ^ 1],
-                    changed + 1, 1, first_rebase);
+                launch_scan<KP, true>(e, N, K, pi, Pi, boundary_in ? boundary_in + K : nullptr, has_next, beta, nullptr,
+                                      fb[cur], fb[cur ^ 1], changed + 1, 1, first_rebase, sb);
                 HGP_LAUNCH_CHECK("hmm backward repair");
                 cudaEventRecord(side->join, sb);
                 cudaStreamWaitEvent(st, side->join, 0);

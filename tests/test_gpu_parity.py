@@ -946,13 +946,14 @@ def test_chunked_hmm_equals_sequential(N, K, sticky, sharp):
         assert hm.rounds >= 2
 
 
-def test_sharded_hmm_emulated_ranks_bitwise():
+@pytest.mark.parametrize("K", [11, 64, 100])      # one chunk per CTA (K <= 32) / eight chunks per CTA on the tensor cores
+def test_sharded_hmm_emulated_ranks_bitwise(K):
     """Beat-sharded smoothing emulated on one GPU: slices scanned from guessed boundary
     messages, boundary exchange repeated until no message moves -> bit-identical to the unsharded scan."""
     import hdpgpc_b200 as hb
     from hdpgpc_b200 import ops
     rng = np.random.default_rng(9)
-    N, K, G = 4000, 11, 4
+    N, G = 4000, 4
     q, tt, st = _hmm_case(rng, N, K, 30.0, 1.5)
     startPi, _ = hb.hdp.expected_log_pi(tt, st, K)
     pi, PiT, Pi, Pc = [cu(a) for a in hb.hdp.hmm_operands(tt, startPi, K)]
