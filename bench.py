@@ -366,24 +366,22 @@ def stage_breakdown(torch, ops, eng, reps=3):
 
 
 def table_stage_breakdown(torch, ops, eng, raw, reps=3):
-    """CUDA events between the kernels of the table build (EStepEngine.update_states: the factorisations of all leads in
-    one launch each, then whitening and packing per lead)."""
+    """CUDA events between the kernels of the table build (EStepEngine.update_states: factors and inverse factors of all
+    leads in one launch, then packing and whitening per lead)."""
     acc = {}
     Sig = torch.cat([t["Sigma"] for t in raw], dim=0)
     add = torch.cat([t["add_diag"] for t in raw]) if all(t.get("add_diag") is not None for t in raw) else None
     for rep in range(reps + 1):          # rep 0 is a warm-up: it allocates the outputs (cudaMalloc stalls between the events)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        Lf, info = ops.chol_batched(Sig, add_diag=add)
+        Lf, W, info = ops.cholinv_batched(Sig, add_diag=add)
         ev[1].record()
-        W = ops.tri_inverse_batched(Lf)
-        ev[2].record()
         off, packed = 0, []
         for tb, t in zip(eng.leads, raw):
             F = t["Sigma"].shape[0]
             packed.append(ops.pack_factors(W[off:off + F]))
             off += F
-        ev[3].record()
+        ev[2].record()
         off = 0
         for tb, t, Wp in zip(eng.leads, raw, packed):
             F = t["Sigma"].shape[0]
@@ -392,11 +390,11 @@ def table_stage_breakdown(torch, ops, eng, raw, reps=3):
             else:
                 ops.whiten_means(t["mu"], W[off:off + F], tb.factor_of_state)
             off += F
-        ev[4].record()
+        ev[3].record()
         torch.cuda.synchronize()
         if rep == 0:
             continue
-        for k, name in enumerate(("chol", "tri_inverse", "pack_factors", "whiten_means")):
+        for k, name in enumerate(("chol+inverse", "pack_factors", "whiten_means")):
             acc[name] = acc.get(name, 0.0) + ev[k].elapsed_time(ev[k + 1]) / reps
     return {k: round(v, 4) for k, v in acc.items()}
 

@@ -20,6 +20,7 @@ PROTOTYPES = {
     "hgp_pack_leads_slice": (_int, [_p, _i64, _int, _int, _p, _i64, _p]),
     "hgp_chol_batched": (_int, [_p, _i64, _int, _p, _dbl, _p, _p, _p, _p]),
     "hgp_tri_inverse_batched": (_int, [_p, _i64, _int, _p, _p]),
+    "hgp_cholinv_batched": (_int, [_p, _i64, _int, _p, _dbl, _p, _p, _p, _p, _p]),
     "hgp_packed_factor_bytes": (_i64, [_int]),
     "hgp_pack_factors": (_int, [_p, _i64, _int, _p, _p]),
     "hgp_tile_beats": (_int, []),

@@ -5,6 +5,7 @@
 // shared memory and the trailing matrix in L2.  tri_inverse_batched produces W = L^{-1} so the
 // Mahalanobis term becomes a single triangular product (see include/hdpgpc_b200.h).
 #include "hgp_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -213,6 +214,236 @@ tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Factor AND inverse factor of one SPD matrix per CTA in a single left-looking sweep (T <= 512): what a table build needs
+// per cluster covariance (hgp_cholinv_batched).  The two kernels above are latency chains: the right-looking Cholesky
+// updates the whole trailing matrix in global memory with scalar FMAs once per 16-column panel (0.80 ms for the 128
+// factors of a cfg4 table build), the substitution for L^-1 walks scalar k loops over global memory (0.94 ms).  Here
+// every panel is two tensor-core products against what is already final:
+//   U          = A[k0:, k0:k1] - L[k0:, 0:k0] L[k0:k1, 0:k0]^T       (the panel, never read again after this)
+//   L[k0:k1,.] = chol(U[0:16]) (one warp, out of registers),  L[k1:, k0:k1] = U[16:] L_kk^-T
+//   W[k0:k1, 0:k0] = -L_kk^-1 (L[k0:k1, 0:k0] W[0:k0, 0:k0]),   W[k0:k1, k0:k1] = L_kk^-1
+// with the 16 x k0 row block L[k0:k1, 0:k0] staged in shared memory as the B operand of the first product and the A
+// operand of the second; each matrix element is read O(T / 16) times through L2 and written once.  256 threads (the
+// register-resident diagonal factorisation wants more than the 128 registers a 512-thread CTA leaves per thread), 16
+// loads in flight per lane.
+constexpr int CI_THREADS = 256;
+constexpr int CI_NB = 16;
+__host__ __device__ inline int ci_ldb(int T) { return ((T + 7) / 8) * 8 + 4; }      // == 4 (mod 8): conflict-free fragments
+__host__ __device__ inline size_t ci_smem_bytes(int T) {
+    const int TP = (T + 15) & ~15;
+    return sizeof(double) * ((size_t)TP * 20 + 2 * (size_t)CI_NB * ci_ldb(T) + 2 * CI_NB * (CI_NB + 1) + 64);
+}
+
+__global__ void __launch_bounds__(CI_THREADS, 1)
+cholinv_kernel(const double* __restrict__ Sigma, int T, const double* __restrict__ add_diag, double jitter_scale,
+               double* __restrict__ Lfac, double* __restrict__ Wout, double* __restrict__ logdet, int* __restrict__ info) {
+    extern __shared__ __align__(16) double ci_smem[];
+    const int TP = (T + 15) & ~15;
+    const int LDB = ci_ldb(T);
+    double* Ps = ci_smem;                          // [TP][20]   the panel U (rows relative to k0)
+    double* Bs = Ps + (size_t)TP * 20;             // [16][LDB]  L[k0:k1, 0:k0]
+    double* Fs = Bs + CI_NB * LDB;                 // [16][LDB]  L[k0:k1, 0:k0] W[0:k0, 0:k0]
+    double* Dk = Fs + CI_NB * LDB;                 // [16][17]   L_kk (+ 1 / diagonal in column 16)
+    double* Wi = Dk + CI_NB * (CI_NB + 1);         // [16][17]   L_kk^-1
+    double* red = Wi + CI_NB * (CI_NB + 1);
+    __shared__ int s_info;
+    __shared__ double s_jit, s_logdet;
+
+    const int64_t f = blockIdx.x;
+    const double* S = Sigma + f * (int64_t)T * T;
+    double* X = Lfac + f * (int64_t)T * T;
+    double* Y = Wout + f * (int64_t)T * T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lk = lane & 3;
+    const double add = add_diag ? add_diag[f] : 0.0;
+
+    // jitter from the mean |diagonal| (GPI_model._chol_spd, GPI_model.py:83-87); strict upper triangles are zero
+    double part = 0.0;
+    for (int i = tid; i < T; i += CI_THREADS) part += fabs(S[(int64_t)i * T + i] + add);
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    if (tid == 0) { s_info = 0; s_logdet = 0.0; }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < CI_THREADS / 32; ++w) tot += red[w];
+        s_jit = jitter_scale * fmax(tot / T, HGP_EPS);
+    }
+    for (int idx = tid; idx < T * T; idx += CI_THREADS) {
+        const int i = idx / T, j = idx - i * T;
+        if (j > i) { X[idx] = 0.0; Y[idx] = 0.0; }
+    }
+    __syncthreads();
+    const double jit = s_jit;
+
+    for (int k0 = 0; k0 < T; k0 += CI_NB) {
+        const int nb = min(CI_NB, T - k0), k1 = k0 + nb;
+        // ---- 1. stage L[k0:k1, 0:k0] (zero rows below a short last block) ----
+        //      one column per thread: the 16 loads of a column are in flight together (a load -> store loop would wait out
+        //      one L2 latency per element)
+        for (int c = tid; c < k0; c += CI_THREADS) {
+            double v[CI_NB];
+#pragma unroll
+            for (int i = 0; i < CI_NB; ++i) v[i] = (i < nb) ? __ldcg(X + (int64_t)(k0 + i) * T + c) : 0.0;
+#pragma unroll
+            for (int i = 0; i < CI_NB; ++i) Bs[i * LDB + c] = v[i];
+        }
+        __syncthreads();
+        // ---- 2. U = sym(A)[k0:, k0:k1] - L[k0:, 0:k0] Bs^T : one 8-row tile per warp trip, two 8-column tiles ----
+        const int nrt = (T - k0 + 7) >> 3;
+        for (int rt = warp; rt < nrt; rt += CI_THREADS / 32) {
+            const int r = k0 + 8 * rt + lr;
+            const double* xr = X + (int64_t)min(r, T - 1) * T;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int kk0 = 0; kk0 < k0; kk0 += 64) {              // 16 loads in flight per lane, then their 32 DMMAs
+                double av[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int kk = kk0 + 4 * u + lk;
+                    av[u] = (r < T && kk < k0) ? __ldcg(xr + kk) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int kk = kk0 + 4 * u;
+                    if (kk < k0) {
+                        dmma884(acc[0][0], acc[0][1], av[u], Bs[lr * LDB + kk + lk]);
+                        dmma884(acc[1][0], acc[1][1], av[u], Bs[(8 + lr) * LDB + kk + lk]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int cl = 8 * j + 2 * lk + e, c = k0 + cl;
+                    double v = 0.0;
+                    if (r < T && c < k1 && c <= r) {
+                        const double a0 = S[(int64_t)r * T + c];
+                        v = (c == r) ? (a0 + add) + jit : 0.5 * (a0 + S[(int64_t)c * T + r]);   // sym() keeps the diagonal
+                        v -= acc[j][e];
+                    }
+                    Ps[(8 * rt + lr) * 20 + cl] = v;
+                }
+        }
+        __syncthreads();
+        // ---- 3. warp 0: factor the diagonal block out of registers and invert it (as hgp_smem_la.cuh, sl_cholinv) ----
+        if (warp == 0) {
+            const int li = lane & 15;
+            double row[CI_NB];
+#pragma unroll
+            for (int cc = 0; cc < CI_NB; ++cc) row[cc] = (li < nb && cc <= li) ? Ps[li * 20 + cc] : (li == cc ? 1.0 : 0.0);
+            double dinv = 1.0;
+            int bad = 0;
+#pragma unroll
+            for (int j = 0; j < CI_NB; ++j) {
+                const double d = __shfl_sync(0xffffffffu, row[j], j);
+                if (!(d > 0.0) && bad == 0) bad = k0 + j + 1;
+                const double sq = sqrt(d);                       // the same operations as the two-kernel path: l = a / sqrt(d)
+                double l = row[j] / sq;
+                if (li == j) { l = sq; dinv = 1.0 / sq; }
+                if (li >= j) row[j] = l;
+#pragma unroll
+                for (int cc = j + 1; cc < CI_NB; ++cc) {
+                    const double lc = __shfl_sync(0xffffffffu, l, cc);
+                    if (li >= cc) row[cc] -= l * lc;
+                }
+            }
+            double dsel = 1.0;
+#pragma unroll
+            for (int cc = 0; cc < CI_NB; ++cc) if (cc == li) dsel = row[cc];
+            double ldg = (li < nb && lane < 16) ? log(dsel) : 0.0;
+            ldg = warp_sum(ldg);
+            if (lane == 0) { s_logdet += 2.0 * ldg; if (bad && s_info == 0) s_info = bad; }
+            if (lane < 16) {
+#pragma unroll
+                for (int cc = 0; cc < CI_NB; ++cc) Dk[li * (CI_NB + 1) + cc] = row[cc];
+                Dk[li * (CI_NB + 1) + CI_NB] = dinv;
+                if (li < nb) {
+#pragma unroll
+                    for (int cc = 0; cc < CI_NB; ++cc) if (cc <= li) X[(int64_t)(k0 + li) * T + k0 + cc] = row[cc];
+                }
+            }
+            __syncwarp();
+            if (lane < CI_NB) {
+                double x[CI_NB];
+#pragma unroll
+                for (int i = 0; i < CI_NB; ++i) {
+                    double v = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int p = 0; p < CI_NB; ++p) if (p < i) v -= Dk[i * (CI_NB + 1) + p] * ((p >= lane) ? x[p] : 0.0);
+                    x[i] = (i >= lane) ? v * Dk[i * (CI_NB + 1) + CI_NB] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < CI_NB; ++i) {
+                    Wi[i * (CI_NB + 1) + lane] = x[i];
+                    if (i < nb && lane < nb && lane <= i) Y[(int64_t)(k0 + i) * T + k0 + lane] = x[i];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 4. L[k1:, k0:k1] = U[16:] L_kk^-T, one thread per row ----
+        for (int r = k1 + tid; r < T; r += CI_THREADS) {
+            double x[CI_NB];
+#pragma unroll
+            for (int p = 0; p < CI_NB; ++p) x[p] = Ps[(r - k0) * 20 + p];
+            double* xo = X + (int64_t)r * T + k0;
+#pragma unroll
+            for (int cc = 0; cc < CI_NB; ++cc) {
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p < CI_NB; ++p) if (p <= cc) v += x[p] * Wi[cc * (CI_NB + 1) + p];
+                if (cc < nb) xo[cc] = v;
+            }
+        }
+        // ---- 5. W[k0:k1, 0:k0] = -L_kk^-1 (Bs W[0:k0, 0:k0]): column tiles over the warps, k from the tile's diagonal ----
+        const int nct = k0 >> 3;
+        for (int ct = warp; ct < nct; ct += CI_THREADS / 32) {
+            const int cs = 8 * ct;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int kk0 = cs; kk0 < k0; kk0 += 64) {
+                double bv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int kk = kk0 + 4 * u + lk;
+                    bv[u] = (kk < k0) ? __ldcg(Y + (int64_t)kk * T + cs + lr) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int kk = kk0 + 4 * u;
+                    if (kk < k0) {
+                        dmma884(acc[0][0], acc[0][1], Bs[lr * LDB + kk + lk], bv[u]);
+                        dmma884(acc[1][0], acc[1][1], Bs[(8 + lr) * LDB + kk + lk], bv[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                Fs[(8 * i + lr) * LDB + cs + 2 * lk] = acc[i][0];
+                Fs[(8 * i + lr) * LDB + cs + 2 * lk + 1] = acc[i][1];
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < k0; c += CI_THREADS) {
+            double x[CI_NB];
+#pragma unroll
+            for (int p = 0; p < CI_NB; ++p) x[p] = Fs[p * LDB + c];
+#pragma unroll
+            for (int i = 0; i < CI_NB; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p < CI_NB; ++p) if (p <= i) v -= Wi[i * (CI_NB + 1) + p] * x[p];
+                if (i < nb) Y[(int64_t)(k0 + i) * T + c] = v;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (logdet) logdet[f] = s_logdet;
+        info[f] = s_info;
+    }
+}
+
 // Packed factor stream for hgp_score_tiles.  Tp = T rounded up to 8, nrb = Tp/8 row blocks.
 // chunk kc (k columns [8kc, 8kc+8)) holds row blocks rb = kc..nrb-1; block (kc, rb) is 32 lanes x 2
 // doubles: element (lane, ks) = W[8 rb + lane/4][8 kc + 4 ks + lane%4], i.e. the A fragments of two
@@ -297,6 +528,27 @@ extern "C" int hgp_tri_inverse_batched(const double* Lfac, int64_t F, int T, dou
     const int groups = nblk >= 16 ? 8 : (nblk >= 8 ? 4 : (nblk >= 4 ? 2 : 1));
     tri_inverse_kernel<<<dim3((unsigned)F, groups), 256, smem, (cudaStream_t)stream>>>(Lfac, T, W);
     HGP_LAUNCH_CHECK("hgp_tri_inverse_batched");
+    return 0;
+}
+
+extern "C" int hgp_cholinv_batched(const double* Sigma, int64_t F, int T, const double* add_diag, double jitter_scale,
+                                   double* Lfac, double* W, double* logdet, int* info, void* stream) {
+    HGP_REQUIRE(F >= 0 && T > 0 && T <= 1024, "hgp_cholinv_batched: need 0 < T <= 1024");
+    if (F == 0) return 0;
+    // the fused sweep pays from T = 128 on (tools/table_bench.py: 2.7x at T = 256, 3.4x at T = 400; at T = 90 its six panels
+    // are slower than the two small kernels) and holds its panels in shared memory up to T = 512
+    if (((T < 128 || T > 512) && !getenv("HGP_CHOLINV_FUSED")) || getenv("HGP_CHOLINV_TWO_KERNELS")) {
+        int rc = hgp_chol_batched(Sigma, F, T, add_diag, jitter_scale, Lfac, logdet, info, stream);
+        if (rc) return rc;
+        return hgp_tri_inverse_batched(Lfac, F, T, W, stream);
+    }
+    HGP_REQUIRE(T <= 512, "hgp_cholinv_batched: the fused kernel holds T <= 512");
+    const size_t smem = ci_smem_bytes(T);
+    cudaError_t e = cudaFuncSetAttribute(cholinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return hgp_status(e, "hgp_cholinv_batched: smem attribute");
+    cholinv_kernel<<<(unsigned)F, CI_THREADS, smem, (cudaStream_t)stream>>>(Sigma, T, add_diag, jitter_scale, Lfac, W, logdet,
+                                                                          info);
+    HGP_LAUNCH_CHECK("hgp_cholinv_batched");
     return 0;
 }
 

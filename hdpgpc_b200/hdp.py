@@ -128,8 +128,7 @@ class LeadTables:
         add_diag [F] (the `first` jitter of the duplicated first-member factors, :527-529).  W / info: factors already
         inverted by the caller (EStepEngine.update_states factorises all leads in one launch)."""
         if W is None:
-            Lf, info = ops.chol_batched(Sigma, add_diag=add_diag)
-            W = ops.tri_inverse_batched(Lf)
+            _, W, info = ops.cholinv_batched(Sigma, add_diag=add_diag)
         self.W = W
         self.mu = mu
         if mu_sm is not None:
@@ -294,8 +293,7 @@ class EStepEngine:
         if any(t.get("add_diag") is not None for t in tables):
             add = torch.cat([t["add_diag"] if t.get("add_diag") is not None
                              else torch.zeros(t["Sigma"].shape[0], dtype=F64, device=Sig.device) for t in tables])
-        Lf, info = ops.chol_batched(Sig, add_diag=add)
-        W_all = ops.tri_inverse_batched(Lf)
+        _, W_all, info = ops.cholinv_batched(Sig, add_diag=add)
         off = 0
         for tb, t in zip(self.leads, tables):
             F = t["Sigma"].shape[0]

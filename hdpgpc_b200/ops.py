@@ -71,6 +71,22 @@ def chol_batched(Sigma, add_diag=None, jitter_scale=1e-8, want_logdet=False):
     return (L, info, logdet) if want_logdet else (L, info)
 
 
+def cholinv_batched(Sigma, add_diag=None, jitter_scale=1e-8, want_logdet=False):
+    """chol_batched + tri_inverse_batched in one launch (hgp_cholinv_batched).  Returns (L, W, info[, logdet])."""
+    lib = _lib_ready()
+    S = _dev(Sigma).contiguous()
+    F, T, _ = S.shape
+    L = torch.empty_like(S)
+    W = torch.empty_like(S)
+    info = torch.empty(F, dtype=I32, device=S.device)
+    logdet = torch.empty(F, dtype=F64, device=S.device) if want_logdet else None
+    if add_diag is not None:
+        add_diag = _dev(add_diag).to(F64).contiguous()
+    check(lib.hgp_cholinv_batched(ptr(S), F, T, ptr(add_diag), float(jitter_scale), ptr(L), ptr(W), ptr(logdet), ptr(info),
+                                  stream_ptr()), "hgp_cholinv_batched")
+    return (L, W, info, logdet) if want_logdet else (L, W, info)
+
+
 def tri_inverse_batched(Lfac):
     lib = _lib_ready()
     Lf = _dev(Lfac).contiguous()

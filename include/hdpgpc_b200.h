@@ -62,6 +62,10 @@ int hgp_chol_batched(const double* Sigma, int64_t F, int T, const double* add_di
  * term d^T Sigma^{-1} d of GPI_model.py:109-113 / :280-285 is |W d|^2 (one triangular product;
  * the reference's cholesky_solve does two). */
 int hgp_tri_inverse_batched(const double* Lfac, int64_t F, int T, double* W, void* stream);
+/* Both at once -- Lfac as hgp_chol_batched, W = Lfac^{-1} -- in one left-looking sweep per matrix on the tensor cores
+ * (128 <= T <= 512; other sizes run the two calls above): the table build of a sweep (one factor per cluster covariance). */
+int hgp_cholinv_batched(const double* Sigma, int64_t F, int T, const double* add_diag, double jitter_scale,
+                        double* Lfac, double* W, double* logdet, int* info, void* stream);
 
 /* Re-order W[F, T, T] into the DMMA-fragment-ordered, k-chunked stream the tile kernel reads
  * with 1-D bulk (TMA) copies.  Bytes per factor: hgp_packed_factor_bytes(T). */

@@ -1065,6 +1065,41 @@ def test_table_build_kernels(T, S):
     assert np.max(np.abs(nu2 - ref2)) < 1e-12 * np.max(np.abs(ref2))
 
 
+@pytest.mark.parametrize("T", [256, 90, 30, 17, 300, 512, 8])
+def test_cholinv_fused_vs_two_kernels_and_numpy(T, monkeypatch):
+    """hgp_cholinv_batched (left-looking sweep on the tensor cores, factor and inverse factor at once) against the
+    right-looking Cholesky + substitution kernels and against numpy: jitter and `first` diagonal rule included, short last
+    panel (T not a multiple of 16), LAPACK-style info on a matrix that is not positive definite."""
+    from hdpgpc_b200 import ops
+    monkeypatch.setenv("HGP_CHOLINV_FUSED", "1")                         # the fused kernel at every size, not only T >= 128
+    rng = np.random.default_rng(T)
+    F = 5
+    Sig = random_spd(rng, F, T, cond=1e5)
+    Sig += 1e-3 * rng.standard_normal(Sig.shape)                         # not exactly symmetric: sym() is part of the op
+    add = np.array([0.0, 0.5, 0.0, 2.0, 0.0])
+    L1, info1, ld1 = ops.chol_batched(cu(Sig), add_diag=cu(add), want_logdet=True)
+    W1 = ops.tri_inverse_batched(L1)
+    L2, W2, info2, ld2 = ops.cholinv_batched(cu(Sig), add_diag=cu(add), want_logdet=True)
+    assert int(torch.count_nonzero(info1)) == 0 and int(torch.count_nonzero(info2)) == 0
+    assert float(torch.max(torch.abs(L2 - L1))) < 1e-12 * float(torch.max(torch.abs(L1)))
+    assert float(torch.max(torch.abs(W2 - W1))) < 1e-10 * float(torch.max(torch.abs(W1)))
+    assert float(torch.max(torch.abs(ld2 - ld1))) < 1e-11 * float(torch.max(torch.abs(ld1)))
+    assert float(torch.max(torch.abs(torch.triu(L2, 1)))) == 0.0 and float(torch.max(torch.abs(torch.triu(W2, 1)))) == 0.0
+    for f in range(F):
+        M_ = 0.5 * (Sig[f] + Sig[f].T)
+        np.fill_diagonal(M_, np.diag(Sig[f]) + add[f])
+        M_ += 1e-8 * max(np.mean(np.abs(np.diag(Sig[f]) + add[f])), 2.220446049250313e-16) * np.eye(T)
+        Lr = np.linalg.cholesky(M_)
+        assert np.max(np.abs(L2[f].cpu().numpy() - Lr)) < 1e-11 * np.max(np.abs(Lr))
+        assert np.max(np.abs(W2[f].cpu().numpy() @ Lr - np.eye(T))) < 1e-9
+    bad = Sig.copy()
+    bad[2] = -np.eye(T)
+    bad[4][T - 1, T - 1] = -1e6
+    _, _, info3 = ops.cholinv_batched(cu(bad), add_diag=cu(add))
+    _, info4 = ops.chol_batched(cu(bad), add_diag=cu(add))
+    assert info3.tolist() == info4.tolist() and info3[2] == 1 and info3[4] == T and info3[0] == 0
+
+
 @pytest.mark.parametrize("M", [40, 100])
 def test_snr_arbitrary_state_map(M):
     """hgp_snr_states accepts ANY snr_state_of: with a random map nearly every beat of a 64-beat tile starts a new run of

@@ -1,0 +1,37 @@
+#!/usr/bin/env python3
+"""Factorisation stage of a table build: hgp_cholinv_batched (one left-looking sweep per matrix) next to the two kernels it
+replaces, CUDA events, best of 5 after a warm-up.  usage: python tools/table_bench.py [out.json]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from hdpgpc_b200 import ops
+os.environ["HGP_CHOLINV_FUSED"] = "1"      # time the fused kernel at every size
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+res = {}
+for F, T in ((128, 256), (4096, 256), (2271, 90), (64, 400)):
+    A = torch.randn((F, T, T), dtype=torch.float64, device="cuda")
+    Sig = A @ A.transpose(1, 2) / T + torch.eye(T, dtype=torch.float64, device="cuda")
+    del A
+    ms_c = timed(lambda: ops.chol_batched(Sig))
+    Lf, _ = ops.chol_batched(Sig)
+    ms_i = timed(lambda: ops.tri_inverse_batched(Lf))
+    ms_f = timed(lambda: ops.cholinv_batched(Sig))
+    fl = F * (2.0 * T ** 3 / 3)                         # T^3/3 each for the factor and its inverse
+    res[f"F{F}_T{T}"] = {"chol_ms": ms_c, "tri_inverse_ms": ms_i, "fused_ms": ms_f, "speedup": (ms_c + ms_i) / ms_f,
+                         "fused_tflops": fl / (ms_f * 1e-3) / 1e12}
+    del Sig, Lf
+line = json.dumps(res)
+print(line)
+if len(sys.argv) > 1:
+    open(sys.argv[1], "w").write(line + "\n")
