@@ -296,6 +296,17 @@ cholinv_kernel(const double* __restrict__ Sigma, int T, const double* __restrict
             const int r = k0 + 8 * rt + lr;
             const double* xr = X + (int64_t)min(r, T - 1) * T;
             double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            // the panel's own entries of sym(A) come from HBM (first touch): fetched before the k loop, used after it
+            double a_rc[2][2], a_cr[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = k0 + 8 * j + 2 * lk + e;
+                    const bool live = r < T && c < k1 && c <= r;
+                    a_rc[j][e] = live ? __ldg(S + (int64_t)r * T + c) : 0.0;
+                    a_cr[j][e] = (live && c != r) ? __ldg(S + (int64_t)c * T + r) : 0.0;
+                }
             for (int kk0 = 0; kk0 < k0; kk0 += 64) {              // 16 loads in flight per lane, then their 32 DMMAs
                 double av[16];
 #pragma unroll
@@ -319,8 +330,8 @@ cholinv_kernel(const double* __restrict__ Sigma, int T, const double* __restrict
                     const int cl = 8 * j + 2 * lk + e, c = k0 + cl;
                     double v = 0.0;
                     if (r < T && c < k1 && c <= r) {
-                        const double a0 = S[(int64_t)r * T + c];
-                        v = (c == r) ? (a0 + add) + jit : 0.5 * (a0 + S[(int64_t)c * T + r]);   // sym() keeps the diagonal
+                        const double a0 = a_rc[j][e];
+                        v = (c == r) ? (a0 + add) + jit : 0.5 * (a0 + a_cr[j][e]);             // sym() keeps the diagonal
                         v -= acc[j][e];
                     }
                     Ps[(8 * rt + lr) * 20 + cl] = v;

@@ -848,6 +848,163 @@ score_pairs_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-state covariances (estimation_limit = None, regime R2): pairs GROUPED BY FACTOR.  The pair kernel above reads a
+// whole factor per (beat, cluster) pair -- 4 T^2 bytes for T^2 + 3T flops -- although all beats between two consecutive
+// members of a cluster score against the same state, i.e. the same factor (round 1: 13 M pairs/s at T = 256 while
+// pulling 3.5 TB/s of factors through L2).  Here the pair list arrives sorted by factor and cut into chunks of at most
+// 32 pairs that share one; a CTA builds the chunk's residuals d = y - mu as the B operand in shared memory (up to four
+// 8-pair tiles) and streams the factor's rows ONCE from global memory as DMMA A fragments, 16 loads in flight per
+// lane, row tiles dealt to the warps in mirrored order so the triangular k loops balance.  A pair's score does not
+// depend on its chunk mates (every output column of the product is computed on its own, in a fixed k order).
+constexpr int SG_MAXP = 32;
+__host__ __device__ inline int sg_ldd(int T) { return ((T + 7) / 8) * 8 + 4; }
+
+__global__ void __launch_bounds__(256)
+score_groups_kernel(const double* __restrict__ Y, int T, const double* __restrict__ mu, const double* __restrict__ W,
+                    const int* __restrict__ state_of, const int* __restrict__ factor_of_state, int M,
+                    const int* __restrict__ pair_n, const int* __restrict__ pair_m, const int* __restrict__ chunk_start,
+                    int64_t n_chunks, double* __restrict__ q) {
+    extern __shared__ __align__(16) double sg_smem[];
+    __shared__ double s_part[8][SG_MAXP];
+    __shared__ int s_factor, s_pn[SG_MAXP], s_pm[SG_MAXP];
+    const int LDD = sg_ldd(T);
+    double* D = sg_smem;                              // [32][LDD] residuals of the chunk's pairs
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int nrt = (T + 7) >> 3;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int p0 = chunk_start[chunk];
+        const int cnt = min(SG_MAXP, chunk_start[chunk + 1] - p0);
+        const int ntl = (cnt + 7) >> 3;
+        __syncthreads();                              // the previous chunk's readers of D / s_part are done
+        // residuals of the chunk's pairs.  Warp w builds rows w, w + 8, w + 16, w + 24: the index chains (pair -> state ->
+        // rows of Y and mu) of its rows are fetched side by side, and the samples travel eight 32-wide slices at a time --
+        // all loads of a batch before its first store (a load -> store loop waits out one memory latency per slice)
+        {
+            const double* yrow[4];
+            const double* mrow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = warp + 8 * j;
+                yrow[j] = mrow[j] = nullptr;
+                if (c < cnt) {
+                    const int n = pair_n[p0 + c], m = pair_m[p0 + c];
+                    const int st = state_of[(int64_t)n * M + m];
+                    yrow[j] = Y + (int64_t)n * T;
+                    mrow[j] = mu + (int64_t)st * T;
+                    if (lane == 0) { s_pn[c] = n; s_pm[c] = m; }
+                    if (c == 0 && lane == 0) s_factor = factor_of_state ? factor_of_state[st] : st;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = warp + 8 * j;
+                if (c >= 8 * ntl) continue;
+                double* drow = D + c * LDD;
+                for (int t0 = 0; t0 < LDD; t0 += 256) {
+                    double yv[8], mv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int t = t0 + 32 * u + lane;
+                        const bool live = yrow[j] != nullptr && t < T;
+                        yv[u] = live ? __ldg(yrow[j] + t) : 0.0;
+                        mv[u] = live ? __ldg(mrow[j] + t) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int t = t0 + 32 * u + lane;
+                        if (t < LDD) drow[t] = yv[u] - mv[u];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const double* Wf = W + (int64_t)s_factor * T * T;
+        double colsum[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) colsum[nt][0] = colsum[nt][1] = 0.0;
+        // The warp's (row tile, 64-wide k batch) units form one sequence; the 16 loads of unit u + 1 are issued before the
+        // DMMAs of unit u, so the factor streams with two batches in flight per lane instead of one memory latency per batch.
+        // Row tiles are dealt in mirrored order (i, i ^ 7 in alternate groups of eight): long and short k loops alternate.
+        const int i_end = (nrt + 7) & ~7;
+        auto tile_of = [&](int i) { return ((i >> 3) & 1) ? (i ^ 7) : i; };
+        auto load_unit = [&](int i, int kk0, double (&av)[16]) {
+            const int rt = tile_of(i);
+            const int r = 8 * rt + lr;
+            const int kend = min(T, 8 * rt + 8);
+            const double* wr = Wf + (int64_t)min(r, T - 1) * T;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int kk = kk0 + 4 * u + lk;
+                av[u] = (rt < nrt && r < T && kk < kend) ? __ldg(wr + kk) : 0.0;
+            }
+        };
+        auto advance = [&](int& i, int& kk0) {          // next unit of this warp (i >= i_end: none left)
+            kk0 += 64;
+            if (tile_of(i) >= nrt || kk0 >= min(T, 8 * tile_of(i) + 8)) { i += 8; kk0 = 0; }
+            while (i < i_end && tile_of(i) >= nrt) i += 8;
+        };
+        int ci = warp, ckk = 0;
+        while (ci < i_end && tile_of(ci) >= nrt) ci += 8;
+        double avA[16], avB[16];
+        if (ci < i_end) load_unit(ci, ckk, avA);
+        double acc[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        auto consume = [&](int i, int kk0, const double (&av)[16]) {
+            const int kend = min(T, 8 * tile_of(i) + 8);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int kk = kk0 + 4 * u;
+                if (kk < kend) {
+                    const double* bp = D + lr * LDD + kk + lk;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+                        if (nt < ntl) dmma884(acc[nt][0], acc[nt][1], av[u], bp[nt * 8 * LDD]);
+                }
+            }
+            if (kk0 + 64 >= kend) {                      // last batch of the row tile: z is complete
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    colsum[nt][0] += acc[nt][0] * acc[nt][0];
+                    colsum[nt][1] += acc[nt][1] * acc[nt][1];
+                    acc[nt][0] = acc[nt][1] = 0.0;
+                }
+            }
+        };
+        while (ci < i_end) {
+            int ni = ci, nkk = ckk;
+            advance(ni, nkk);
+            if (ni < i_end) load_unit(ni, nkk, avB);
+            consume(ci, ckk, avA);
+            if (ni >= i_end) break;
+            ci = ni; ckk = nkk;
+            advance(ni, nkk);
+            if (ni < i_end) load_unit(ni, nkk, avA);
+            consume(ci, ckk, avB);
+            ci = ni; ckk = nkk;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double v = colsum[nt][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (lane < 4) s_part[warp][nt * 8 + 2 * lane + e] = v;
+            }
+        __syncthreads();
+        if (tid < cnt) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_part[w][tid];
+            q[(int64_t)s_pn[tid] * M + s_pm[tid]] = -0.5 * tot - 0.5 * (double)T * HGP_LOG2PI;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // SNR statistic: one warp per beat, looping clusters; smoothed means gathered through L1/L2
 // ------------------------------------------------------------------------------------------
 template <int NREG>   // NREG = ceil(T / 32) <= 8: the beat lives in registers
@@ -1356,6 +1513,27 @@ extern "C" int hgp_score_pairs(const double* Y, int64_t N, int T, const double* 
     score_pairs_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(Y, N, T, mu, W, state_of, factor_of_state,
                                                                           M, pair_n, pair_m, n_pairs, q);
     HGP_LAUNCH_CHECK("hgp_score_pairs");
+    return 0;
+}
+
+extern "C" int hgp_score_groups_max_pairs(void) { return SG_MAXP; }
+
+extern "C" int hgp_score_groups(const double* Y, int64_t N, int T, const double* mu, const double* W, const int* state_of,
+                                const int* factor_of_state, int M, const int* pair_n, const int* pair_m,
+                                const int* chunk_start, int64_t n_chunks, double* q, void* stream) {
+    HGP_REQUIRE(N >= 0 && T > 0 && M >= 0 && n_chunks >= 0, "hgp_score_groups: bad sizes");
+    HGP_REQUIRE(T <= 512, "hgp_score_groups: need T <= 512");
+    HGP_REQUIRE(pair_n != nullptr && pair_m != nullptr && chunk_start != nullptr, "hgp_score_groups: pair lists required");
+    if (n_chunks == 0) return 0;
+    const size_t smem = sizeof(double) * (size_t)SG_MAXP * sg_ldd(T);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(score_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return hgp_status(e, "hgp_score_groups: smem attribute");
+    }
+    const int blocks = (int)hgp_min64(n_chunks, 148 * 4);
+    score_groups_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(Y, T, mu, W, state_of, factor_of_state, M, pair_n, pair_m,
+                                                                       chunk_start, n_chunks, q);
+    HGP_LAUNCH_CHECK("hgp_score_groups");
     return 0;
 }
 

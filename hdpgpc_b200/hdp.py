@@ -8,6 +8,8 @@ slice; `EStepEngine.sweep()` is what bench.py times.  Beats shard by contiguous 
 ranks (`torch.distributed`, NCCL): cluster tables are broadcast, the HMM boundary messages are
 all-gathered, the statistics all-reduced.
 """
+import os
+
 import numpy as np
 import torch
 from scipy.special import digamma
@@ -92,6 +94,7 @@ class LeadTables:
         self.factor_of_cluster = None
         self.pair_n = self.pair_m = None
         self._whiten_plan = None
+        self._group_plan = None
         self.use_tiles = False
         self.block_path = T > 256                   # beats longer than the tile kernel's 256 rows: hgp_score_blocks
         if tile_path is None:
@@ -167,7 +170,13 @@ class LeadTables:
                 ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self.pair_n, self.pair_m,
                                 out=out)
         else:
-            ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, out=out)
+            # per-state covariances (estimation_limit=None): pairs grouped by factor, one factor read per group
+            if self.T <= 512 and not os.environ.get("HGP_NO_GROUPS"):
+                if self._group_plan is None:
+                    self._group_plan = ops.group_plan(self.state_of, self.factor_of_state)
+                ops.score_groups(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, self._group_plan, out=out)
+            else:
+                ops.score_pairs(self.Y, self.mu, self.W, self.state_of, self.factor_of_state, out=out)
             if snr_out is not None and self.snr_state_of is not None:
                 self.snr(snr_out)
         return out
@@ -368,11 +377,17 @@ class EStepEngine:
             self._stage = torch.empty((N, T, L), dtype=F64, device=dev)
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._Yp = torch.empty((L, N, T), dtype=F64, device=dev)
+            self._copy_stream.wait_stream(torch.cuda.current_stream())    # the fresh staging block may be a recycled one
+            self._stage_free = None
         for ld, tb in enumerate(self.leads):
             tb.Y = self._Yp[ld]
         bounds = self.slice_bounds(N, n_slices, growth)
         main = torch.cuda.current_stream()
-        self._copy_stream.wait_stream(main)          # earlier sweeps are done with the staging buffer
+        # The copies wait for the previous call's last reader of the staging buffer only -- not for whatever else is queued
+        # on the compute stream: a table build (update_states) issued just before this call then runs UNDER the first
+        # copies instead of in front of them.
+        if getattr(self, "_stage_free", None) is not None:
+            self._copy_stream.wait_event(self._stage_free)
         events = []
         with torch.cuda.stream(self._copy_stream):
             for n0, n1 in bounds:
@@ -383,6 +398,9 @@ class EStepEngine:
         for (n0, n1), ev in zip(bounds, events):
             main.wait_event(ev)
             ops.pack_leads_slice(self._stage[n0:n1], self._Yp, n0)
+            if n1 == N:
+                self._stage_free = torch.cuda.Event()
+                self._stage_free.record(main)
             for ld, tb in enumerate(self.leads):
                 tb.score_slice(n0, n1, self.q[ld], self.snr[ld] if self.use_snr else None)
         for ld, tb in enumerate(self.leads):

@@ -219,6 +219,54 @@ def score_pairs(Y, mu, W, state_of, factor_of_state, pair_n=None, pair_m=None, o
     return q
 
 
+def group_plan(state_of, factor_of_state, pair_n=None, pair_m=None):
+    """Work lists of hgp_score_groups: the (beat, cluster) pairs with a state, sorted by factor and cut into chunks of at
+    most hgp_score_groups_max_pairs() pairs that share one.  Depends on the index maps only (re-usable across sweeps).
+    Returns dict(pair_n, pair_m, chunk_start, n_chunks, invalid) -- invalid: flat indices into q of pairs without a state."""
+    lib = _lib_ready()
+    so = _dev(state_of).to(I32).contiguous()
+    N, M = so.shape
+    dev = so.device
+    if pair_n is None:
+        flat = torch.arange(N * M, device=dev)
+    else:
+        flat = _dev(pair_n).long() * M + _dev(pair_m).long()
+    st = so.reshape(-1)[flat].long()
+    ok = st >= 0
+    invalid = flat[~ok]
+    flat, st = flat[ok], st[ok]
+    fac = st if factor_of_state is None else _dev(factor_of_state).long()[st]
+    order = torch.argsort(fac, stable=True)
+    flat, fac = flat[order], fac[order]
+    n = flat.numel()
+    mp = int(lib.hgp_score_groups_max_pairs())
+    if n == 0:
+        z = torch.zeros(1, dtype=I32, device=dev)
+        return dict(pair_n=z, pair_m=z, chunk_start=z, n_chunks=0, invalid=invalid)
+    idx = torch.arange(n, device=dev)
+    new_grp = torch.ones(n, dtype=torch.bool, device=dev)
+    new_grp[1:] = fac[1:] != fac[:-1]
+    grp_first = torch.cummax(torch.where(new_grp, idx, torch.zeros_like(idx)), dim=0).values      # start of each pair's group
+    starts = torch.nonzero(((idx - grp_first) % mp) == 0).reshape(-1)
+    chunk_start = torch.cat([starts, torch.tensor([n], device=dev)]).to(I32).contiguous()
+    return dict(pair_n=(flat // M).to(I32).contiguous(), pair_m=(flat % M).to(I32).contiguous(), chunk_start=chunk_start,
+                n_chunks=int(starts.numel()), invalid=invalid)
+
+
+def score_groups(Y, mu, W, state_of, factor_of_state, plan, out=None):
+    """score_pairs for a whole plane whose pairs are grouped by factor (hgp_score_groups; plan = group_plan(...))."""
+    lib = _lib_ready()
+    N, T = Y.shape
+    M = state_of.shape[1]
+    q = out if out is not None else torch.zeros((N, M), dtype=F64, device=Y.device)
+    check(lib.hgp_score_groups(ptr(Y), N, T, ptr(mu), ptr(W), ptr(state_of), ptr(factor_of_state), M, ptr(plan["pair_n"]),
+                               ptr(plan["pair_m"]), ptr(plan["chunk_start"]), plan["n_chunks"], ptr(q), stream_ptr()),
+          "hgp_score_groups")
+    if plan["invalid"].numel():
+        q.view(-1)[plan["invalid"]] = 0.0            # "cluster has no members" (GPI_model.py:494-495)
+    return q
+
+
 def snr_states(Y, mu_sm, snr_state_of, out=None):
     lib = _lib_ready()
     N, T = Y.shape

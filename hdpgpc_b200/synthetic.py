@@ -153,10 +153,9 @@ def build_engine(wl, group=None, tile_path=None, sharded=None):
     Yp = ops.pack_leads(wl["Y"])
     leads = []
     for ld, tb in enumerate(wl["leads"]):
-        Lf, info = ops.chol_batched(tb["Sigma"], add_diag=tb["add_diag"])
+        _, W, info = ops.cholinv_batched(tb["Sigma"], add_diag=tb["add_diag"])     # as EStepEngine.update_states does
         if int(torch.count_nonzero(info)):
             raise LinAlgError("synthetic covariance not SPD")
-        W = ops.tri_inverse_batched(Lf)
         leads.append(LeadTables(Yp[ld], tb["mu"], W, tb["state_of"], tb["factor_of_state"], tb["mu_sm"],
                                 tb["snr_state_of"], tile_path=tile_path))
     return EStepEngine(leads, wl["transTheta"], wl["startTheta"], group=group, sharded=sharded)

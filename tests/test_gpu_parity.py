@@ -881,6 +881,39 @@ def test_tiles_vs_pairs_vs_oracle(N, T, L, M):
     assert rel(eng_t.q, eng_p.q) < 1e-11
 
 
+@pytest.mark.parametrize("T,S,F", [(90, 40, 40), (256, 12, 5), (33, 7, 7), (300, 9, 4)])
+def test_grouped_pairs_equal_pair_kernel(T, S, F):
+    """hgp_score_groups (pairs sorted by factor, one factor read per chunk of <= 32 pairs, tensor cores) against the pair
+    kernel on a random state map: factors shared by several states, groups longer than one chunk, pairs without a state,
+    an explicit pair list."""
+    from hdpgpc_b200 import ops
+    rng = np.random.default_rng(T + S)
+    N, M = 150, 6
+    Sig = random_spd(rng, F, T, cond=1e3)
+    Lf, info = ops.chol_batched(cu(Sig))
+    W = ops.tri_inverse_batched(Lf)
+    Y = cu(rng.standard_normal((N, T)) * 10.0)
+    mu = cu(rng.standard_normal((S, T)) * 10.0)
+    so = rng.integers(-1, S, size=(N, M)).astype(np.int32)
+    so[:100, 0] = 3                                                      # one state (factor) scoring 100 beats: 4 chunks
+    fos = cu(np.arange(S) % F, torch.int32)
+    so_d = cu(so, torch.int32)
+    want = ops.score_pairs(Y, mu, W, so_d, fos)
+    plan = ops.group_plan(so_d, fos)
+    assert plan["n_chunks"] >= F and int(plan["invalid"].numel()) == int((so < 0).sum())
+    cs = plan["chunk_start"].cpu().numpy()
+    assert np.all(np.diff(cs) <= 32) and np.all(np.diff(cs) >= 1) and cs[-1] == int((so >= 0).sum())
+    got = ops.score_groups(Y, mu, W, so_d, fos, plan, out=torch.full((N, M), 7.0, dtype=torch.float64, device="cuda"))
+    assert float(torch.max(torch.abs(got - want) / torch.clamp(torch.abs(want), min=1.0))) < 1e-11
+    assert torch.all(got[so_d < 0] == 0.0)
+    pn = cu(np.array([5, 9, 9, 140]), torch.int32); pm = cu(np.array([0, 1, 0, 5]), torch.int32)
+    plan2 = ops.group_plan(so_d, fos, pn, pm)
+    got2 = ops.score_groups(Y, mu, W, so_d, fos, plan2, out=torch.full((N, M), 7.0, dtype=torch.float64, device="cuda"))
+    sel = torch.zeros((N, M), dtype=torch.bool, device="cuda"); sel[pn.long(), pm.long()] = True
+    assert torch.all(got2[~sel] == 7.0)
+    assert float(torch.max(torch.abs(got2[sel] - torch.where(so_d < 0, torch.zeros_like(want), want)[sel]))) < 1e-9
+
+
 def test_empty_cluster_scores_zero():
     from hdpgpc_b200 import synthetic
     wl = synthetic.make_workload(90, T=32, L=1, M=3, seed=3)
