@@ -646,13 +646,16 @@ def run_ours(args):
         except Exception:
             pass
         traffic = traffic_source = None   # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu capture
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_score_tiles_ncu.json")))
-            if args.config == "cfg4" and B == CFG["beats_per_gpu"]:
-                traffic = prof["dram_bytes_per_launch"]
-                traffic_source = "ncu --set full capture of this kernel at this shape, profiles/r01_score_tiles_ncu.json (not re-measured in this run)"
-        except Exception:
-            pass
+        for tag in ("r02", "r01"):       # the latest committed capture of this kernel at this shape
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_score_tiles_ncu.json")))
+                if args.config == "cfg4" and B == CFG["beats_per_gpu"]:
+                    traffic = prof["dram_bytes_per_launch"]
+                    traffic_source = (f"ncu --set full capture of this kernel at this shape, profiles/{tag}_score_tiles_ncu.json "
+                                      "(tools/gpu_round.sh; not re-measured in this run)")
+                break
+            except Exception:
+                continue
         bytes_launch = r["bytes_launch"]
         cpu = None
         if not args.no_cpu and world == 1:          # the CPU baseline is reported by the single-GPU run only

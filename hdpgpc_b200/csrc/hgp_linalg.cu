@@ -227,7 +227,10 @@ tri_inverse_kernel(const double* __restrict__ Lfac, int T, double* __restrict__ 
 // operand of the second; each matrix element is read O(T / 16) times through L2 and written once.  256 threads (the
 // register-resident diagonal factorisation wants more than the 128 registers a 512-thread CTA leaves per thread), 16
 // loads in flight per lane.
-constexpr int CI_THREADS = 256;
+#ifndef HGP_CI_THREADS
+#define HGP_CI_THREADS 256
+#endif
+constexpr int CI_THREADS = HGP_CI_THREADS;
 constexpr int CI_NB = 16;
 __host__ __device__ inline int ci_ldb(int T) { return ((T + 7) / 8) * 8 + 4; }      // == 4 (mod 8): conflict-free fragments
 __host__ __device__ inline size_t ci_smem_bytes(int T) {

@@ -16,7 +16,8 @@ echo "bench rc=$?"
 cut -c1-600 gpurun_out/bench_${TAG}.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_ref.json 2> gpurun_out/bench_${TAG}_ref.err
 echo "ref rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_${TAG}.csv \
+OURS='regex:score_tiles|score_pairs|score_groups|score_blocks|snr_|lead_weights|hmm_scan|hard_resp|stats_|cholinv|chol_kernel|tri_inverse|pack_|whiten|tile_uniform'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-peak --no-cfg5 --no-fit > gpurun_out/ncu_${TAG}.log 2>&1
 echo "launch list rc=$?"
 if [ -n "$FULL" ]; then

@@ -19,10 +19,14 @@ unit = data[0][ix["Metric Unit"]]
 scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6}[unit]
 vals = [float(r[ix["Metric Value"]].replace(",", "")) * scale for r in data]
 ends = [i for i, n in enumerate(names) if "stats_finish" in n]
-lo, hi = ends[-2] + 1, ends[-1] + 1
+# the last sweep that is device-resident (no table build, no host slices in it) and the last end-to-end call
+ranges = [(ends[k] + 1, ends[k + 1] + 1) for k in range(len(ends) - 1)]
+resident = [r for r in ranges if not any(("pack_leads" in n or "cholinv" in n or "chol_kernel" in n) for n in names[r[0]:r[1]])]
+e2e_rng = [r for r in ranges if any("pack_leads" in n for n in names[r[0]:r[1]])]
+lo, hi = resident[-1] if resident else ranges[-1]
 tot = sum(vals[lo:hi])
 out = [f"# {tag} — ncu launch list of one device-resident E-step sweep (cfg4: 100k beats x 256 x 2 leads, 64 clusters)", "",
-       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<our kernels> -c 200 --csv python bench.py --steps 2 --warmup 3 --no-cpu --no-peak`",
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<our kernels> -c 400 --csv python bench.py --steps 2 --warmup 3 --no-cpu --no-peak --no-cfg5 --no-fit` (tools/gpu_round.sh)",
        "(per-launch times under ncu are serialised / cold-cache: compare SHARES, not absolutes; the bench value is taken without ncu)", "",
        "| launch | kernel | ms | share |", "|---|---|---|---|"]
 agg = collections.Counter()
@@ -36,7 +40,21 @@ for n, ms in agg.most_common():
 r = bench["roofline"]
 out += ["", f"Same sweep timed live by `bench.py` without ncu (CUDA events): {bench['ms_per_step']:.2f} ms per step, score_tiles_kernel "
         f"{r['kernel_ms']:.2f} ms per launch x 2 leads = {100 * r['kernel_share_of_step']:.1f} % of the step "
-        f"(ncu share {100 * agg['score_tiles_kernel'] / tot:.1f} %).", ""]
+        f"(ncu share {100 * sum(v for k, v in agg.items() if k.startswith('score_tiles_kernel')) / tot:.1f} %).", ""]
+if e2e_rng:
+    lo2, hi2 = e2e_rng[-1]
+    tot2 = sum(vals[lo2:hi2])
+    out += ["## The end-to-end call of the same run (`EStepEngine.update_states` + `sweep_from_host`: table build, four host slices)", "",
+            "| launch | kernel | ms | share |", "|---|---|---|---|"]
+    agg2 = collections.Counter()
+    for i in range(lo2, hi2):
+        out.append(f"| {i} | {names[i]} | {vals[i]:.3f} | {100 * vals[i] / tot2:.1f}% |")
+        agg2[names[i]] += vals[i]
+    out.append(f"| | **total** | {tot2:.3f} | |")
+    out += ["", "Aggregated:", "", "| kernel | ms | share |", "|---|---|---|"]
+    for n, ms in agg2.most_common():
+        out.append(f"| {n} | {ms:.3f} | {100 * ms / tot2:.1f}% |")
+    out.append("")
 open(f"profiles/{tag}_launches.md", "w").write("\n".join(out))
 
 # ---- full capture of the tile kernel
@@ -56,7 +74,7 @@ want = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.a
         "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 d = {}
 md = [f"# {tag} — `ncu --set full` of score_tiles_kernel (one cfg4 lead plane: 100k beats x 64 clusters, T=256)", "",
-      "Command: `ncu --set full --clock-control none --import-source on -k regex:score_tiles -s 6 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu --no-peak`", "",
+      "Command: `ncu --set full --clock-control none --import-source on -k regex:score_tiles_kernel -s 4 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu --no-peak --no-cfg5 --no-fit` (tools/gpu_round.sh)", "",
       "| metric | unit | value |", "|---|---|---|"]
 for w in want:
     for i, name in enumerate(h):
@@ -71,11 +89,14 @@ json.dump({"kernel": "score_tiles_kernel", "workload": "cfg4 lead plane: 100000 
 md += ["", f"DRAM traffic per launch = {rd + wr:.1f} MB (read {rd:.1f} + write {wr:.1f}); algorithmic bytes "
        f"{r['hbm']['algorithmic_bytes_per_launch'] / 1e6:.1f} MB (beats + whitened means + scores + state map + packed factors) -> no re-reads.",
        "FP64 tensor instruction = `DMMA.8x8x4` (SASS), factor stream = `UBLKCP` (TMA bulk copy), `USETMAXREG` alloc/dealloc per warpgroup.",
-       f"Tensor pipe active {d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']} % of the cycles (76 % at the start of the round, `gpurun_out/prof_tiles_r01.ncu-rep`).", ""]
-hist = "profiles/r01_tile_kernel_history.md"
-try:
-    md += open(hist).read().splitlines()
-except FileNotFoundError:
-    pass
+       f"Tensor pipe active {d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']} % of the cycles.", ""]
+if tag == "r01":
+    try:
+        md += open("profiles/r01_tile_kernel_history.md").read().splitlines()
+    except FileNotFoundError:
+        pass
+else:
+    md += ["The kernel's scoring instantiation is the one of round 1 (`profiles/r01_tile_kernel_history.md` lists the variants tried);",
+           "round 2 added a second instantiation (`score_tiles_kernel<true>`) that turns the same pipeline into the table build's whitening.", ""]
 open(f"profiles/{tag}_score_tiles_ncu.md", "w").write("\n".join(md) + "\n")
 print("wrote profiles for", tag)
