@@ -534,10 +534,68 @@ def _timed(key, fn):
     return wrapper
 
 
-def enable(gpi_model_cls=None, gpi_hdp_cls=None, igp_cls=None, profile=False):
+def tune_host_allocator():
+    """Keep freed host memory mapped (glibc mallopt: no trimming, no mmap per large block).  With the numerics on the
+    device the reference's drivers spend their host time on short-lived megabyte tensors (the (N, K, K) respPair of every
+    `variational_local_terms`, the (N, M) score planes): glibc hands such blocks back to the kernel on free and maps
+    fresh pages for the next one, and a page fault inside a microVM costs microseconds -- `torch.full((500, 441))` was
+    measured at 2.2 ms inside an online fit against 8 us in isolation.  Process-wide and optional; returns True if applied."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_TOP_PAD, M_MMAP_THRESHOLD = -1, -2, -3
+        ok = libc.mallopt(M_MMAP_THRESHOLD, 32 << 20) and libc.mallopt(M_TRIM_THRESHOLD, 1 << 30) and \
+            libc.mallopt(M_TOP_PAD, 64 << 20)
+        return bool(ok)
+    except Exception:
+        return False
+
+
+_host_threads_saved = {}
+
+
+def _limit_host_threads(n, blas=1):
+    """With the numerics on the device, what is left on the host are the reference's own small tensor operations (LogLik
+    over an (N, K, K) respPair, the L-BFGS of the HDP weights in scipy).  Sixteen-thread OpenMP and BLAS pools waking up
+    for 200 k-element tensors -- and spinning against each other between calls -- cost milliseconds per operation:
+    record 100 online, 500 beats: `torch.max` 19.5 s of a 93 s fit with the defaults, 0.23 s with the pools limited
+    (fit 93 -> 50 s).  Limits torch's intra-op pool to `n` threads and the BLAS pools to one; `disable()` restores both."""
+    import os
+    if os.environ.get("HGP_HOST_THREADS"):              # A/B override: "0" = leave alone, "4" / "4,1" = torch[,blas]
+        parts = os.environ["HGP_HOST_THREADS"].split(",")
+        n = int(parts[0]) or None
+        blas = int(parts[1]) if len(parts) > 1 else blas
+    if n is None or _host_threads_saved:
+        return
+    _host_threads_saved["torch"] = torch.get_num_threads()
+    torch.set_num_threads(max(1, min(int(n), _host_threads_saved["torch"])))
+    if blas:
+        try:
+            import threadpoolctl
+            _host_threads_saved["blas"] = threadpoolctl.threadpool_limits(int(blas), user_api="blas")
+        except Exception:
+            pass
+
+
+def _restore_host_threads():
+    if "torch" in _host_threads_saved:
+        torch.set_num_threads(_host_threads_saved["torch"])
+    lim = _host_threads_saved.get("blas")
+    if lim is not None:
+        try:
+            lim.restore_original_limits()
+        except Exception:
+            pass
+    _host_threads_saved.clear()
+
+
+def enable(gpi_model_cls=None, gpi_hdp_cls=None, igp_cls=None, profile=False, host_threads=4):
     """Patch the reference classes (found in `hdpgpc.GPI_model` / `hdpgpc.GPI_HDP` / `hdpgpc.GPI` unless given).
-    profile=True accumulates calls and wall seconds per seam method in `seam_times`."""
+    profile=True accumulates calls and wall seconds per seam method in `seam_times`.  host_threads: size of torch's
+    intra-op CPU pool while the patch is active (BLAS pools go to one thread; None leaves both alone) -- see
+    `_limit_host_threads`."""
     import importlib
+    _limit_host_threads(host_threads)
     gpi_model_cls = gpi_model_cls or importlib.import_module("hdpgpc.GPI_model").GPI_model
     gpi_hdp_cls = gpi_hdp_cls or importlib.import_module("hdpgpc.GPI_HDP").GPI_HDP
     igp_cls = igp_cls or importlib.import_module("hdpgpc.GPI").IterativeGaussianProcess
@@ -556,3 +614,4 @@ def disable():
     for key in [k for k in _saved if not k.endswith("/cls")]:
         cls = _saved.pop(key + "/cls")
         setattr(cls, key.split(".", 1)[1], _saved.pop(key))
+    _restore_host_threads()

@@ -41,6 +41,14 @@ def run_on_device(name, quiet=True, profile=False):
     import hdpgpc.GPI as gpi
     import hdpgpc.GPI_model as gm
     hgi.seam_times.clear()
+    if os.environ.get("HGP_TUNE_MALLOC"):
+        hgi.tune_host_allocator()
+    if os.environ.get("HGP_FIT_TORCH_THREADS"):
+        import torch
+        torch.set_num_threads(int(os.environ["HGP_FIT_TORCH_THREADS"]))
+    if os.environ.get("HGP_FIT_BLAS_THREADS"):
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(int(os.environ["HGP_FIT_BLAS_THREADS"]), user_api="blas")
     hgi.enable(gm.GPI_model, hdp.GPI_HDP, gpi.IterativeGaussianProcess, profile=profile)
     launches0 = hb.ops.launch_count()
     try:
