@@ -31,7 +31,7 @@ PROTOTYPES = {
     "hgp_score_blocks": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p]),
     "hgp_score_pairs": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _i64, _p, _p]),
     "hgp_score_groups_max_pairs": (_int, []),
-    "hgp_score_groups": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _p, _i64, _p, _p]),
+    "hgp_score_groups": (_int, [_p, _i64, _int, _p, _p, _p, _p, _int, _p, _p, _p, _i64, _int, _p, _p]),
     "hgp_snr_states": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p]),
     "hgp_mean_beat_work_doubles": (_i64, [_int]),
     "hgp_mean_beat": (_int, [_p, _i64, _int, _p, _p, _p]),

@@ -859,14 +859,18 @@ score_pairs_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
 constexpr int SG_MAXP = 32;
 __host__ __device__ inline int sg_ldd(int T) { return ((T + 7) / 8) * 8 + 4; }
 
+// NT = 8-pair tiles per chunk (2 or 4: chunks of <= 16 or <= 32 pairs).  A DMMA that is merely predicated off still occupies
+// the FP64 tensor pipe (ncu on the first version: pipe 55 % busy, much of it on tiles without pairs), so the plan picks
+// NT = 2 when factors rarely score more than 16 pairs.
+template <int NT>
 __global__ void __launch_bounds__(256)
 score_groups_kernel(const double* __restrict__ Y, int T, const double* __restrict__ mu, const double* __restrict__ W,
                     const int* __restrict__ state_of, const int* __restrict__ factor_of_state, int M,
                     const int* __restrict__ pair_n, const int* __restrict__ pair_m, const int* __restrict__ chunk_start,
                     int64_t n_chunks, double* __restrict__ q) {
     extern __shared__ __align__(16) double sg_smem[];
-    __shared__ double s_part[8][SG_MAXP];
-    __shared__ int s_factor, s_pn[SG_MAXP], s_pm[SG_MAXP];
+    __shared__ double s_part[8][8 * NT];
+    __shared__ int s_factor, s_pn[8 * NT], s_pm[8 * NT];
     const int LDD = sg_ldd(T);
     double* D = sg_smem;                              // [32][LDD] residuals of the chunk's pairs
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -874,17 +878,17 @@ score_groups_kernel(const double* __restrict__ Y, int T, const double* __restric
     const int nrt = (T + 7) >> 3;
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int p0 = chunk_start[chunk];
-        const int cnt = min(SG_MAXP, chunk_start[chunk + 1] - p0);
+        const int cnt = min(8 * NT, chunk_start[chunk + 1] - p0);
         const int ntl = (cnt + 7) >> 3;
         __syncthreads();                              // the previous chunk's readers of D / s_part are done
         // residuals of the chunk's pairs.  Warp w builds rows w, w + 8, w + 16, w + 24: the index chains (pair -> state ->
         // rows of Y and mu) of its rows are fetched side by side, and the samples travel eight 32-wide slices at a time --
         // all loads of a batch before its first store (a load -> store loop waits out one memory latency per slice)
         {
-            const double* yrow[4];
-            const double* mrow[4];
+            const double* yrow[NT];
+            const double* mrow[NT];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NT; ++j) {
                 const int c = warp + 8 * j;
                 yrow[j] = mrow[j] = nullptr;
                 if (c < cnt) {
@@ -897,7 +901,7 @@ score_groups_kernel(const double* __restrict__ Y, int T, const double* __restric
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NT; ++j) {
                 const int c = warp + 8 * j;
                 if (c >= 8 * ntl) continue;
                 double* drow = D + c * LDD;
@@ -920,9 +924,9 @@ score_groups_kernel(const double* __restrict__ Y, int T, const double* __restric
         }
         __syncthreads();
         const double* Wf = W + (int64_t)s_factor * T * T;
-        double colsum[4][2];
+        double colsum[NT][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) colsum[nt][0] = colsum[nt][1] = 0.0;
+        for (int nt = 0; nt < NT; ++nt) colsum[nt][0] = colsum[nt][1] = 0.0;
         // The warp's (row tile, 64-wide k batch) units form one sequence; the 16 loads of unit u + 1 are issued before the
         // DMMAs of unit u, so the factor streams with two batches in flight per lane instead of one memory latency per batch.
         // Row tiles are dealt in mirrored order (i, i ^ 7 in alternate groups of eight): long and short k loops alternate.
@@ -948,9 +952,9 @@ score_groups_kernel(const double* __restrict__ Y, int T, const double* __restric
         while (ci < i_end && tile_of(ci) >= nrt) ci += 8;
         double avA[16], avB[16];
         if (ci < i_end) load_unit(ci, ckk, avA);
-        double acc[4][2];
+        double acc[NT][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
         auto consume = [&](int i, int kk0, const double (&av)[16]) {
             const int kend = min(T, 8 * tile_of(i) + 8);
 #pragma unroll
@@ -959,13 +963,13 @@ score_groups_kernel(const double* __restrict__ Y, int T, const double* __restric
                 if (kk < kend) {
                     const double* bp = D + lr * LDD + kk + lk;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
+                    for (int nt = 0; nt < NT; ++nt)
                         if (nt < ntl) dmma884(acc[nt][0], acc[nt][1], av[u], bp[nt * 8 * LDD]);
                 }
             }
             if (kk0 + 64 >= kend) {                      // last batch of the row tile: z is complete
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
+                for (int nt = 0; nt < NT; ++nt) {
                     colsum[nt][0] += acc[nt][0] * acc[nt][0];
                     colsum[nt][1] += acc[nt][1] * acc[nt][1];
                     acc[nt][0] = acc[nt][1] = 0.0;
@@ -985,7 +989,7 @@ score_groups_kernel(const double* __restrict__ Y, int T, const double* __restric
             ci = ni; ckk = nkk;
         }
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 double v = colsum[nt][e];
@@ -1520,19 +1524,21 @@ extern "C" int hgp_score_groups_max_pairs(void) { return SG_MAXP; }
 
 extern "C" int hgp_score_groups(const double* Y, int64_t N, int T, const double* mu, const double* W, const int* state_of,
                                 const int* factor_of_state, int M, const int* pair_n, const int* pair_m,
-                                const int* chunk_start, int64_t n_chunks, double* q, void* stream) {
+                                const int* chunk_start, int64_t n_chunks, int max_pairs, double* q, void* stream) {
+    HGP_REQUIRE(max_pairs == 16 || max_pairs == 32, "hgp_score_groups: max_pairs (pairs per chunk) must be 16 or 32");
     HGP_REQUIRE(N >= 0 && T > 0 && M >= 0 && n_chunks >= 0, "hgp_score_groups: bad sizes");
     HGP_REQUIRE(T <= 512, "hgp_score_groups: need T <= 512");
     HGP_REQUIRE(pair_n != nullptr && pair_m != nullptr && chunk_start != nullptr, "hgp_score_groups: pair lists required");
     if (n_chunks == 0) return 0;
-    const size_t smem = sizeof(double) * (size_t)SG_MAXP * sg_ldd(T);
+    const size_t smem = sizeof(double) * (size_t)max_pairs * sg_ldd(T);
+    auto kern = max_pairs == 16 ? score_groups_kernel<2> : score_groups_kernel<4>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(score_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return hgp_status(e, "hgp_score_groups: smem attribute");
     }
     const int blocks = (int)hgp_min64(n_chunks, 148 * 4);
-    score_groups_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(Y, T, mu, W, state_of, factor_of_state, M, pair_n, pair_m,
-                                                                       chunk_start, n_chunks, q);
+    kern<<<blocks, 256, smem, (cudaStream_t)stream>>>(Y, T, mu, W, state_of, factor_of_state, M, pair_n, pair_m, chunk_start,
+                                                       n_chunks, q);
     HGP_LAUNCH_CHECK("hgp_score_groups");
     return 0;
 }

@@ -302,12 +302,13 @@ class EStepEngine:
         if any(t.get("add_diag") is not None for t in tables):
             add = torch.cat([t["add_diag"] if t.get("add_diag") is not None
                              else torch.zeros(t["Sigma"].shape[0], dtype=F64, device=Sig.device) for t in tables])
-        _, W_all, info = ops.cholinv_batched(Sig, add_diag=add)
-        off = 0
-        for tb, t in zip(self.leads, tables):
-            F = t["Sigma"].shape[0]
-            tb.update_states(t["mu"], None, None, t.get("mu_sm"), W=W_all[off:off + F], info=info[off:off + F])
-            off += F
+        with ops.nvtx("table_build"):
+            _, W_all, info = ops.cholinv_batched(Sig, add_diag=add)
+            off = 0
+            for tb, t in zip(self.leads, tables):
+                F = t["Sigma"].shape[0]
+                tb.update_states(t["mu"], None, None, t.get("mu_sm"), W=W_all[off:off + F], info=info[off:off + F])
+                off += F
         bad = torch.count_nonzero(info).reshape(1)
         self._table_info = bad          # checked lazily (check_tables) so that the build stays asynchronous
         return self
@@ -321,16 +322,19 @@ class EStepEngine:
     # -- pieces --
     def score_all(self):
         for ld, tb in enumerate(self.leads):
-            tb.score(self.q[ld], self.snr[ld] if self.use_snr else None)
+            with ops.nvtx(f"score[lead {ld}]"):
+                tb.score(self.q[ld], self.snr[ld] if self.use_snr else None)
         return self.q, self.snr
 
     def responsibilities(self):
-        qbar, e, w, flags = ops.lead_weights(self.q, self.snr if self.use_snr else None, self.lead_w)
-        if self.world == 1:
-            hm = ops.hmm_smooth(e, self.pi, self.PiT, self.Pi, self.Pc, workspace=self._hmm_ws)
-            self.boundary_rounds = 0
-        else:
-            hm = self._hmm_sharded(e)
+        with ops.nvtx("lead_weights"):
+            qbar, e, w, flags = ops.lead_weights(self.q, self.snr if self.use_snr else None, self.lead_w)
+        with ops.nvtx("hmm_smooth"):
+            if self.world == 1:
+                hm = ops.hmm_smooth(e, self.pi, self.PiT, self.Pi, self.Pc, workspace=self._hmm_ws)
+                self.boundary_rounds = 0
+            else:
+                hm = self._hmm_sharded(e)
         self.hmm_rounds = hm.rounds
         return qbar, e, w, hm
 

@@ -11,6 +11,26 @@ from ._lib import check, ptr, stream_ptr
 F64 = torch.float64
 I32 = torch.int32
 
+_NVTX = bool(os.environ.get("HGP_NVTX"))
+
+
+class nvtx:
+    """NVTX range around a stage of the path (HGP_NVTX=1; shows up in `ncu --nvtx` / Nsight timelines): the stages of a
+    sweep (table build, scoring per lead, responsibilities, statistics), chain replays, hyper-fits, warp fits."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push("hgp:" + self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 def _lib_ready():
     _lib.require_cuda()
@@ -219,7 +239,7 @@ def score_pairs(Y, mu, W, state_of, factor_of_state, pair_n=None, pair_m=None, o
     return q
 
 
-def group_plan(state_of, factor_of_state, pair_n=None, pair_m=None):
+def group_plan(state_of, factor_of_state, pair_n=None, pair_m=None, max_pairs=None):
     """Work lists of hgp_score_groups: the (beat, cluster) pairs with a state, sorted by factor and cut into chunks of at
     most hgp_score_groups_max_pairs() pairs that share one.  Depends on the index maps only (re-usable across sweeps).
     Returns dict(pair_n, pair_m, chunk_start, n_chunks, invalid) -- invalid: flat indices into q of pairs without a state."""
@@ -242,7 +262,14 @@ def group_plan(state_of, factor_of_state, pair_n=None, pair_m=None):
     mp = int(lib.hgp_score_groups_max_pairs())
     if n == 0:
         z = torch.zeros(1, dtype=I32, device=dev)
-        return dict(pair_n=z, pair_m=z, chunk_start=z, n_chunks=0, invalid=invalid)
+        return dict(pair_n=z, pair_m=z, chunk_start=z, n_chunks=0, invalid=invalid, max_pairs=mp)
+    if max_pairs is None:
+        # chunks of 16 unless most pairs sit in groups that fill more than two 8-pair tiles: an idle tile still costs
+        # tensor-pipe time, a second chunk of the same factor costs a (mostly L2-served) second read of it
+        sizes = torch.bincount(fac)
+        in_large = sizes[sizes > 16].sum()
+        max_pairs = mp if int(in_large) * 2 > n else 16
+    mp = int(max_pairs)
     idx = torch.arange(n, device=dev)
     new_grp = torch.ones(n, dtype=torch.bool, device=dev)
     new_grp[1:] = fac[1:] != fac[:-1]
@@ -250,7 +277,7 @@ def group_plan(state_of, factor_of_state, pair_n=None, pair_m=None):
     starts = torch.nonzero(((idx - grp_first) % mp) == 0).reshape(-1)
     chunk_start = torch.cat([starts, torch.tensor([n], device=dev)]).to(I32).contiguous()
     return dict(pair_n=(flat // M).to(I32).contiguous(), pair_m=(flat % M).to(I32).contiguous(), chunk_start=chunk_start,
-                n_chunks=int(starts.numel()), invalid=invalid)
+                n_chunks=int(starts.numel()), invalid=invalid, max_pairs=mp)
 
 
 def score_groups(Y, mu, W, state_of, factor_of_state, plan, out=None):
@@ -260,7 +287,7 @@ def score_groups(Y, mu, W, state_of, factor_of_state, plan, out=None):
     M = state_of.shape[1]
     q = out if out is not None else torch.zeros((N, M), dtype=F64, device=Y.device)
     check(lib.hgp_score_groups(ptr(Y), N, T, ptr(mu), ptr(W), ptr(state_of), ptr(factor_of_state), M, ptr(plan["pair_n"]),
-                               ptr(plan["pair_m"]), ptr(plan["chunk_start"]), plan["n_chunks"], ptr(q), stream_ptr()),
+                               ptr(plan["pair_m"]), ptr(plan["chunk_start"]), plan["n_chunks"], int(plan["max_pairs"]), ptr(q), stream_ptr()),
           "hgp_score_groups")
     if plan["invalid"].numel():
         q.view(-1)[plan["invalid"]] = 0.0            # "cluster has no members" (GPI_model.py:494-495)
@@ -450,7 +477,8 @@ def chain_run(descs, T, pipeline=None):
             setattr(arr[i], name, v)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     dev = host.cuda()
-    check(lib.hgp_chain_run_ex(ptr(dev), n, T, int(pipeline), stream_ptr()), "hgp_chain_run_ex")
+    with nvtx(f"chain_run[{n} chains, T={T}, pipeline={int(pipeline)}]"):
+        check(lib.hgp_chain_run_ex(ptr(dev), n, T, int(pipeline), stream_ptr()), "hgp_chain_run_ex")
     torch.cuda.current_stream().synchronize()
     return keep
 

@@ -116,12 +116,13 @@ int hgp_score_pairs(const double* Y, int64_t N, int T, const double* mu, const d
                     const int* pair_n, const int* pair_m, int64_t n_pairs, double* q, void* stream);
 /* The same scores with the pairs GROUPED BY FACTOR (per-state covariances, estimation_limit = None): pair_n / pair_m
  * sorted so that pairs of one factor are adjacent, chunk_start[c] .. chunk_start[c + 1] (n_chunks + 1 entries) = the pairs
- * of chunk c, at most hgp_score_groups_max_pairs() of them, all with the same factor (every pair must have a state >= 0).
- * One CTA streams the chunk's factor once and scores all its pairs on the tensor cores; T <= 512. */
+ * of chunk c, at most max_pairs of them (16 or 32 = hgp_score_groups_max_pairs(): two or four 8-pair tiles per chunk; 16
+ * when factors rarely score more pairs -- idle tiles still cost tensor-pipe time), all with the same factor (every pair
+ * must have a state >= 0).  One CTA streams the chunk's factor once and scores all its pairs on the tensor cores; T <= 512. */
 int hgp_score_groups_max_pairs(void);
 int hgp_score_groups(const double* Y, int64_t N, int T, const double* mu, const double* W, const int* state_of,
                      const int* factor_of_state, int M, const int* pair_n, const int* pair_m, const int* chunk_start,
-                     int64_t n_chunks, double* q, void* stream);
+                     int64_t n_chunks, int max_pairs, double* q, void* stream);
 
 /* ---- lead weighting: GPI_HDP.compute_snr (GPI_HDP.py:732-748), weight_mean (:685-701),
  *      LogLik (:632-661) ------------------------------------------------------------------

@@ -974,7 +974,13 @@ def test_chunked_hmm_equals_sequential(N, K, sticky, sharp):
     for t in dz:
         v = np.sort(alpha[t] * beta[t])[::-1]
         assert v[1] > v[0] * (1 - 1e-9)
-    assert np.mean(hm.zpair.cpu().numpy() == zp) > 0.999
+    # the pair arg-max likewise: exact, except where the oracle's best two pairs are within 1e-9 relative of each other
+    eb = O._safe_exp_rows(q_norm) * beta
+    dzp = np.nonzero(hm.zpair.cpu().numpy() != zp)[0]
+    for t in dzp:
+        v = np.sort((alpha[t - 1][:, None] * eb[t][None, :] * Pc).reshape(-1))[::-1]
+        assert v[1] > v[0] * (1 - 1e-9), (t, v[:2])
+    assert len(dzp) <= max(2, N // 500), len(dzp)            # and ties at that level are rare
     if sticky > 1000:
         assert hm.rounds >= 2
 
