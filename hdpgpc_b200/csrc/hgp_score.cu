@@ -520,13 +520,14 @@ score_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double*
 // straight from their row-major layout (B[k][c] = Y[n0 + c][k]), the triangular K loop cut at the row tile's diagonal,
 // and the whitened mean subtracted / squared / summed per beat in registers, so z never goes to memory.  Every
 // (tile, cluster) item is computed the same way whatever N is: a sliced sweep stays bitwise equal to the resident one.
-constexpr int SB = 64, SBK = 16, SBA_PITCH = 20, SBB_PITCH = 72;
+constexpr int SB = 64, SBK = 32, SB_PITCH = 36;        // pitch == 4 (mod 8): fragment loads of a half-warp hit 16 banks
+constexpr int SB_TILE = SB * SB_PITCH;                   // doubles per operand tile
+__host__ __device__ inline size_t sb_smem_bytes() { return sizeof(double) * 4 * SB_TILE; }   // A and B, double-buffered
 __global__ void __launch_bounds__(256)
 score_blocks_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ nu,
                     const double* __restrict__ W, const int* __restrict__ state_of,
                     const int* __restrict__ factor_of_cluster, int M, double* __restrict__ q) {
-    __shared__ double As[SB * SBA_PITCH];
-    __shared__ double Bs[SBK * SBB_PITCH];
+    extern __shared__ __align__(16) double sb_smem[];    // [2][A tile | B tile]: both stored [row or beat][k]
     __shared__ double s_col[4][SB];
     __shared__ int s_state[SB];
     __shared__ int s_any;
@@ -556,6 +557,8 @@ score_blocks_kernel(const double* __restrict__ Y, int64_t N, int T, const double
 #pragma unroll
     for (int j = 0; j < 4; ++j) colsum[j][0] = colsum[j][1] = 0.0;
     const int nrt = (T + SB - 1) / SB;
+    // thread (ld_r, ld_k): rows / beats ld_r + 8 u, samples ld_k of the 32-wide chunk -- consecutive lanes walk a row
+    const int ld_k = tid & 31, ld_r = tid >> 5;
     for (int rt = 0; rt < nrt; ++rt) {
         const int r0 = rt * SB;
         double acc[2][4][2];
@@ -564,43 +567,64 @@ score_blocks_kernel(const double* __restrict__ Y, int64_t N, int T, const double
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         const int kmax = min(T, r0 + SB);      // W is lower triangular: columns past the row tile's diagonal are zero
-        // operands of the next K chunk travel from global memory into registers under the current chunk's DMMAs
-        double ra[4], rb[4];
+        // this warp's 16 rows end at their own diagonal: chunks past it (and row groups past the last row of a short tail
+        // tile) multiply zeros only and are skipped behind a warp-uniform branch -- 97 % of the executed products are
+        // useful at T = 400 instead of the 72 % of a 64-row granularity
+        const int kend_w = (r0 + 16 * wm < T) ? min(kmax, r0 + 16 * wm + 16) : 0;
+        // operands of chunk c + 1 travel global -> registers under the DMMAs of chunk c and land in the OTHER shared
+        // buffer: one barrier per 32-wide chunk (64 DMMAs per warp between barriers)
+        double ra[8], rb[8];
         auto gload = [&](int k0) {
+            const int gk = k0 + ld_k;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = tid + 256 * u;
-                const int r = idx / SBK, k = idx % SBK;
-                const int gr = r0 + r, gk = k0 + k;
+            for (int u = 0; u < 8; ++u) {
+                const int gr = r0 + ld_r + 8 * u;
                 ra[u] = (gr < T && gk <= gr) ? __ldg(Wm + (int64_t)gr * T + gk) : 0.0;
-                const int c = idx / SBK;                     // consecutive threads walk a beat's samples (contiguous)
-                const int64_t n = n0 + c;
+                const int64_t n = n0 + ld_r + 8 * u;
                 rb[u] = (gk < T && n < N) ? __ldg(Y + n * T + gk) : 0.0;
             }
         };
+        auto sstore = [&](int buf) {
+            double* As = sb_smem + buf * 2 * SB_TILE;
+            double* Bs = As + SB_TILE;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                As[(ld_r + 8 * u) * SB_PITCH + ld_k] = ra[u];
+                Bs[(ld_r + 8 * u) * SB_PITCH + ld_k] = rb[u];
+            }
+        };
+        __syncthreads();                       // the previous row tile's readers are done with both buffers
         gload(0);
-        for (int k0 = 0; k0 < kmax; k0 += SBK) {
+        sstore(0);
+        int buf = 0;
+        for (int k0 = 0; k0 < kmax; k0 += SBK, buf ^= 1) {
+            __syncthreads();                   // chunk k0 is in `buf`; everybody has left buffer buf ^ 1 (chunk k0 - 32)
+            const bool more = k0 + SBK < kmax;
+            if (more) gload(k0 + SBK);
+            if (k0 < kend_w) {
+                const double* As = sb_smem + buf * 2 * SB_TILE;
+                const double* Bs = As + SB_TILE;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = tid + 256 * u;
-                As[(idx / SBK) * SBA_PITCH + idx % SBK] = ra[u];
-                Bs[(idx % SBK) * SBB_PITCH + idx / SBK] = rb[u];
+                for (int h = 0; h < 2; ++h) {
+                    if (k0 + 16 * h < kend_w) {          // kend_w is a multiple of 16: a real branch around 32 DMMAs
+#pragma unroll
+                        for (int ks = 4 * h; ks < 4 * h + 4; ++ks) {
+                            double a[2], bf[4];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                a[i] = As[(16 * wm + 8 * i + (lane >> 2)) * SB_PITCH + 4 * ks + (lane & 3)];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                bf[j] = Bs[(32 * wn + 8 * j + (lane >> 2)) * SB_PITCH + 4 * ks + (lane & 3)];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+                        }
+                    }
+                }
             }
-            __syncthreads();
-            if (k0 + SBK < kmax) gload(k0 + SBK);
-#pragma unroll
-            for (int ks = 0; ks < SBK / 4; ++ks) {
-                double a[2], bf[4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) a[i] = As[(16 * wm + 8 * i + (lane >> 2)) * SBA_PITCH + 4 * ks + (lane & 3)];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * ks + (lane & 3)) * SBB_PITCH + 32 * wn + 8 * j + (lane >> 2)];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
-            }
-            __syncthreads();
+            if (more) sstore(buf ^ 1);
         }
         // element (row = r0 + 16 wm + 8 i + lane/4, beat = 32 wn + 8 j + 2 (lane%4) + e): z = acc - nu[state][row]
 #pragma unroll
@@ -1500,7 +1524,9 @@ extern "C" int hgp_score_blocks(const double* Y, int64_t N, int T, const double*
     if (M > 65535) { hgp_set_error("hgp_score_blocks: M <= 65535 (got %d)", M); return HGP_E_UNSUPPORTED; }
     if (N == 0 || M == 0) return 0;
     const dim3 grid((unsigned)((N + SB - 1) / SB), (unsigned)M);
-    score_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, N, T, nu, W, state_of, factor_of_cluster, M, q);
+    cudaError_t e = cudaFuncSetAttribute(score_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem_bytes());
+    if (e != cudaSuccess) return hgp_status(e, "hgp_score_blocks: smem attribute");
+    score_blocks_kernel<<<grid, 256, sb_smem_bytes(), (cudaStream_t)stream>>>(Y, N, T, nu, W, state_of, factor_of_cluster, M, q);
     HGP_LAUNCH_CHECK("hgp_score_blocks");
     return 0;
 }
