@@ -1206,27 +1206,48 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
         const int nb = (int)hgp_min64(SNRM_BT, N - n0);
         __syncthreads();                     // previous tile's readers are done
         // ---- beat tile in B-fragment order + sum y^2 per beat; state indices of the tile
-        for (int c = warp; c < SNRM_BT; c += 8) {
-            const int64_t n = n0 + c;
-            double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
-            double p = 0.0, v[8];
+        //      (a warp's eight rows in two passes of four: 32 loads in flight per lane, not one memory latency per row)
+#pragma unroll 1
+        for (int c0 = warp; c0 < SNRM_BT; c0 += 32) {
+            double v[4][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {        // all loads of the row in flight at once (T <= 256)
-                const int t = lane + 32 * k;
-                v[k] = (c < nb && t < T) ? __ldg(Y + n * T + t) : 0.0;
+            for (int q = 0; q < 4; ++q) {
+                const int c = c0 + 8 * q;
+                const int64_t n = n0 + c;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int t = lane + 32 * k;
+                    v[q][k] = (c < nb && t < T) ? __ldg(Y + n * T + t) : 0.0;
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int t = lane + 32 * k;
-                if (t < nrb * 8) base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = v[k];
-                p += v[k] * v[k];
+            for (int q = 0; q < 4; ++q) {
+                const int c = c0 + 8 * q;
+                double* base = Yfrag + ((c >> 3) * 32 + (c & 7) * 4) * 2;
+                double p = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int t = lane + 32 * k;
+                    if (t < nrb * 8) base[(t >> 3) * Y_CHUNK_DOUBLES + (t & 3) * 2 + ((t >> 2) & 1)] = v[q][k];
+                    p += v[q][k] * v[q][k];
+                }
+                p = warp_sum(p);
+                if (lane == 0) ysq[c] = p;
             }
-            p = warp_sum(p);
-            if (lane == 0) ysq[c] = p;
         }
-        for (int i = tid; i < SNRM_BT * M; i += 256) {
-            const int b = i / M;
-            sstate[i] = (b < nb) ? snr_state_of[n0 * M + i] : -3;        // -3: beat outside the sequence, matches no row
+        //      state indices: eight loads in flight per thread
+        for (int i0 = tid; i0 < SNRM_BT * M; i0 += 256 * 8) {
+            int sv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 256 * u;
+                sv[u] = (i < SNRM_BT * M && i / M < nb) ? snr_state_of[n0 * M + i] : -3;   // -3: outside the sequence
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 256 * u;
+                if (i < SNRM_BT * M) sstate[i] = sv[u];
+            }
         }
         __syncthreads();
         // ---- rows: one per distinct state of every cluster
@@ -1239,10 +1260,20 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
             cnt[tid] = c;
         }
         __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int m = 0; m < M; ++m) { const int c = cnt[m]; cnt[m] = acc; acc += c; }
-            cnt[M] = acc;
+        if (warp == 0) {                     // exclusive prefix sum over the clusters (M <= 128: four per lane + a warp scan)
+            int c4[4], tot = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int m = 4 * lane + u; c4[u] = (m < M) ? cnt[m] : 0; tot += c4[u]; }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            int run = incl - tot;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int m = 4 * lane + u; if (m < M) cnt[m] = run; run += c4[u]; }
+            if (lane == 31) cnt[M] = incl;
         }
         __syncthreads();
         const int n_rows = cnt[M];

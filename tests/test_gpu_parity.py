@@ -948,7 +948,9 @@ def _hmm_case(rng, N, K, sticky, sharp):
 
 @pytest.mark.parametrize("N,K,sticky,sharp", [(3000, 5, 5.0, 8.0), (1000, 37, 0.0, 3.0), (2049, 128, 50.0, 2.0),
                                               (5000, 3, 2000.0, 0.05), (600, 64, 10.0, 30.0), (257, 1, 1.0, 1.0),
-                                              (1500, 24, 3.0, 4.0), (900, 12, 1.0, 2.0)])   # KP = 32 / 16 instantiations
+                                              (1500, 24, 3.0, 4.0), (900, 12, 1.0, 2.0),   # KP = 32 / 16 instantiations
+                                              (5, 40, 1.0, 2.0), (256, 64, 5.0, 1.0), (2, 33, 0.0, 1.0),   # eight-chunk kernel:
+                                              (513, 100, 500.0, 0.1)])   # fewer chunks than the CTA holds, one beat past a chunk, slow mixing
 def test_chunked_hmm_equals_sequential(N, K, sticky, sharp):
     """Multi-chunk scans (N > 256) incl. a slowly mixing chain (sticky=2000, flat emissions) that needs
     several repair rounds; result must equal the sequential oracle."""
