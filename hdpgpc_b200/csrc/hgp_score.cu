@@ -1181,6 +1181,12 @@ snr_tiles_kernel(const double* __restrict__ Y, int64_t N, int T, const double* _
 //     the row's state; noise = sum mu^2 - 2 cross + sum y^2, recomputed directly in the rare case where the expansion
 //     would cancel more than eight digits (SNR > 80 dB).
 constexpr int SNRM_BT = 64;
+// doubles behind the beat tile: the four A stages, or what the epilogue's [NROW][65] cross-term exchange needs beyond the
+// beat tile it overlays, whichever is larger
+__host__ __device__ inline size_t snr_ast_doubles(int nrb, int rbw) {
+    const size_t stages = 4 * 8 * (size_t)rbw * 64, tile = (size_t)nrb * 512, exch = 64 * (size_t)rbw * 65;
+    return exch > tile + stages ? exch - tile : stages;
+}
 template <int RBW>   // row blocks per warp: 2 (M <= 64) or 3 (M <= 128)
 __global__ void __launch_bounds__(256, 1)
 snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __restrict__ mu_sm,
@@ -1190,8 +1196,8 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
     extern __shared__ __align__(16) unsigned char smraw[];
     const int nrb = (T + 7) / 8;            // k-chunks
     double* Yfrag = reinterpret_cast<double*>(smraw);                    // [nrb][512]
-    double* Ast = Yfrag + nrb * Y_CHUNK_DOUBLES;                         // [4][NRB][64]
-    double* ysq = Ast + 4 * NRB * 64;                                    // [64]
+    double* Ast = Yfrag + nrb * Y_CHUNK_DOUBLES;                         // [4][NRB][64] (+ room for the epilogue's exchange)
+    double* ysq = Ast + snr_ast_doubles(nrb, RBW);                       // [64]
     double* row_sig = ysq + SNRM_BT;                                     // [NROW]
     int* row_s = reinterpret_cast<int*>(row_sig + NROW);                 // [NROW]
     int* row_m = row_s + NROW;                                           // [NROW]
@@ -1306,6 +1312,7 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
             for (int b = 0; b < nb; ++b) {
                 const int sb = sstate[b * M + tid];
                 if (sb != prev) { row_s[r] = sb; row_m[r] = tid; ++r; prev = sb; }
+                sstate[b * M + tid] = r - 1;         // from here on: the ROW of the pair (its state is row_s[row])
             }
         }
         for (int r = n_rows + tid; r < NROW; r += 256) { row_s[r] = -1; row_m[r] = -1; }
@@ -1380,34 +1387,42 @@ snr_mma_kernel(const double* __restrict__ Y, int64_t N, int T, const double* __r
             if (lane == 0) row_sig[warp + 8 * i] = tot;
         }
         __syncthreads();
-        // ---- epilogue
+        // ---- epilogue.  The cross terms leave the registers through shared memory (over the beat tile and the A stages, both
+        //      dead now), so that every (beat, cluster) pair is finished by exactly one thread with its neighbours in m: no
+        //      divergent search for "which beats of my row block belong to my row", one log10 per pair instead of one
+        //      predicated pass per accumulator, and the stores to snr[n][m] are coalesced (ncu: a third of the kernel sat here).
+        double* Cs = reinterpret_cast<double*>(smraw);                     // [NROW][65]
 #pragma unroll
         for (int j = 0; j < RBW; ++j) {
             const int r = (warp + 8 * j) * 8 + (lane >> 2);
-            const int m = row_m[r], sr = row_s[r];
-            const double sig = row_sig[r];
-            if (m < 0) continue;
+            if (r < n_rows) {
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = nt * 8 + 2 * (lane & 3) + e;
-                    if (sstate[c * M + m] != sr) continue;               // also rejects beats outside the sequence
-                    double out = 0.0;
-                    if (sr >= 0) {
-                        double noi = sig - 2.0 * acc[j][nt][e] + ysq[c];
-                        if (noi < 1e-8 * (sig + ysq[c])) {
-                            // the expansion would lose more than eight digits (the dB value would be off by more than
-                            // 4e-8 absolute at 80 dB): direct sum for this pair
-                            const double* mr = mu_sm + (int64_t)sr * T;
-                            const double* yr = Y + (n0 + c) * T;
-                            noi = 0.0;
-                            for (int t = 0; t < T; ++t) { const double d = mr[t] - yr[t]; noi += d * d; }
-                        }
-                        out = 10.0 * log10((sig + HGP_EPS) / (noi + HGP_EPS));
-                    }
-                    snr[(n0 + c) * M + m] = out;
+                for (int nt = 0; nt < 8; ++nt) {
+                    Cs[r * 65 + nt * 8 + 2 * (lane & 3)] = acc[j][nt][0];
+                    Cs[r * 65 + nt * 8 + 2 * (lane & 3) + 1] = acc[j][nt][1];
                 }
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < nb * M; p += 256) {
+            const int c = p / M;
+            const int r = sstate[p];
+            const int sr = row_s[r];
+            double out = 0.0;
+            if (sr >= 0) {
+                const double sig = row_sig[r];
+                double noi = sig - 2.0 * Cs[r * 65 + c] + ysq[c];
+                if (noi < 1e-8 * (sig + ysq[c])) {
+                    // the expansion would lose more than eight digits (the dB value would be off by more than
+                    // 4e-8 absolute at 80 dB): direct sum for this pair
+                    const double* mr = mu_sm + (int64_t)sr * T;
+                    const double* yr = Y + (n0 + c) * T;
+                    noi = 0.0;
+                    for (int t = 0; t < T; ++t) { const double d = mr[t] - yr[t]; noi += d * d; }
+                }
+                out = 10.0 * log10((sig + HGP_EPS) / (noi + HGP_EPS));
+            }
+            snr[n0 * M + p] = out;
         }
     }
 }
@@ -1615,7 +1630,7 @@ extern "C" int hgp_snr_states(const double* Y, int64_t N, int T, const double* m
         const int nrbk = (T + 7) / 8;
         const int rbw = M <= 64 ? 2 : 3;
         const int nrow = 64 * rbw;
-        const size_t msm = sizeof(double) * ((size_t)nrbk * Y_CHUNK_DOUBLES + 4 * 8 * rbw * 64 + SNRM_BT + nrow) +
+        const size_t msm = sizeof(double) * ((size_t)nrbk * Y_CHUNK_DOUBLES + snr_ast_doubles(nrbk, rbw) + SNRM_BT + nrow) +
                            sizeof(int) * (2 * (size_t)nrow + ((M + 2) & ~1) + (size_t)SNRM_BT * M) + 16;
         auto kern = rbw == 2 ? snr_mma_kernel<2> : snr_mma_kernel<3>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
