@@ -400,7 +400,7 @@ def table_stage_breakdown(torch, ops, eng, raw, reps=3):
 
 
 def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, warmup, rank, world, local, with_clocks,
-                   with_e2e=True):
+                   with_e2e=True, h2d_gbs=None):
     """One workload: device-resident sweep (`value`), table build, end-to-end call from pinned host beats."""
     T, L, M, B = cfg["T"], cfg["L"], cfg["M"], cfg["beats_per_gpu"]
     wl = synthetic.make_workload(B, T=T, L=L, M=M, seed=1234, device="cuda", n_offset=rank * B, N_total=world * B)
@@ -500,6 +500,8 @@ def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, w
 
     # ---- end-to-end leg: cluster states + host beats in, labels + statistics out ----
     if with_e2e:
+        # slice schedule from the two rates measured above (this rank's H2D rate with all ranks copying, the sweep time)
+        out["slices"] = list(eng.tune_slices(h2d_gbs, ms_max)) if h2d_gbs else None
         def e2e_step():
             # the public end-to-end call: table build from (mu, Sigma), pinned host beats in (sliced H2D copies overlapped
             # with scoring), labels and statistics back on the host
@@ -617,7 +619,8 @@ def run_ours(args):
         t_ = torch.tensor([h2d_gbs], dtype=torch.float64, device="cuda")
         dist.all_reduce(t_, op=dist.ReduceOp.MIN)
         h2d_gbs = float(t_)
-    r = measure_config(args, torch, dist, hb, ops, synthetic, cfg, SCALING, args.steps, args.warmup, rank, world, local, True)
+    r = measure_config(args, torch, dist, hb, ops, synthetic, cfg, SCALING, args.steps, args.warmup, rank, world, local, True,
+                       h2d_gbs=h2d_gbs)
     ms, ms_max, tile_ms, table_ms, e2e_ms = r["ms"], r["ms_max"], r["tile_ms"], r["table_ms"], r["e2e_ms"]
 
     # ---- second leg: BASELINE.json configs[4] (2M beats x 256 x 128 clusters, strong scaling), 3 sweeps ----
@@ -679,7 +682,8 @@ def run_ours(args):
                                  "peak_gbs": mp.get("hbm_gbs"), "frac": (bytes_launch / (tile_ms * 1e-3) / 1e9) / mp["hbm_gbs"] if mp.get("hbm_gbs") else None}},
             "cpu_baseline": cpu,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                    "ms_per_step": e2e_ms, "includes": "table build from (mu, Sigma) + H2D of the beats + sweep + D2H of labels / statistics"},
+                    "ms_per_step": e2e_ms, "includes": "table build from (mu, Sigma) + H2D of the beats + sweep + D2H of labels / statistics",
+                    "slices": r.get("slices")},
             "host": {"numa_binding_rank0": numa, "h2d_gbs_per_rank_min": h2d_gbs,
                      "h2d_note": "pinned host -> device, 256 MiB, all ranks copying at the same time, slowest rank"},
             "cfg5": cfg5,

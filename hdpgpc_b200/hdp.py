@@ -366,11 +366,29 @@ class EStepEngine:
         edges = [0] + [min(N, c * tile) for c in cuts]
         return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
 
-    def sweep_from_host(self, Y_host, n_slices=4, growth=4.0):
+    def tune_slices(self, h2d_gbs, sweep_ms, first_fraction=0.03):
+        """Choose the slice schedule of `sweep_from_host` from two measured rates: the host-to-device rate this rank gets
+        (GB/s, with every rank of the node copying at once) and the time of a device-resident sweep.  A slice may be
+        `growth` times longer than its predecessor only if a beat still copies `growth` times faster than it scores; with
+        eight ranks sharing the host the copy rate halves (55 -> 29 GB/s per rank on the 8 x B200 box) and the 1 : 4 : 16 : 64
+        schedule of a lone rank leaves the last slice waiting for its data (end to end 40.5 ms against 31.4 ms alone)."""
+        N, L, T = self.N, self.L, self.leads[0].T
+        copy_ms = N * T * L * 8 / (float(h2d_gbs) * 1e9) * 1e3
+        growth = min(4.0, max(1.25, 0.85 * float(sweep_ms) / max(copy_ms, 1e-9)))
+        n = 1
+        while sum(growth ** k for k in range(n)) * first_fraction < 1.0 and n < 12:
+            n += 1
+        self._slice_cfg = (n, growth)
+        return self._slice_cfg
+
+    def sweep_from_host(self, Y_host, n_slices=None, growth=None):
         """The end-to-end public call: beats arrive in host memory (pinned for an asynchronous copy) in the reference's
         [N, T, L] layout (tests/test_offline.py:31), labels and statistics go back to the host.  The beats are cut into
         tile-aligned slices (`slice_bounds`); the host-to-device copy of slice k+1 runs on a copy stream under the
-        scoring of slice k."""
+        scoring of slice k.  Slice schedule: the arguments, else what `tune_slices` chose, else 4 slices growing 4x."""
+        cfg = getattr(self, "_slice_cfg", None) or (4, 4.0)
+        n_slices = cfg[0] if n_slices is None else n_slices
+        growth = cfg[1] if growth is None else growth
         N, L, T = self.N, self.L, self.leads[0].T
         if tuple(Y_host.shape) != (N, T, L):
             raise HgpError(f"sweep_from_host: expected beats of shape {(N, T, L)}, got {tuple(Y_host.shape)}")

@@ -1176,6 +1176,13 @@ def test_sweep_from_host_equals_resident_sweep(N, T):
     out = eng.sweep_from_host(Y_host, n_slices=3)
     assert torch.equal(eng.q, q_ref)
     assert torch.equal(out["z_host"], z_ref.cpu()) and torch.equal(out["stats_host"], packed_ref.cpu())
+    # the schedule chosen from measured rates (slow host link: many nearly equal slices; fast link: few, growing 4x)
+    for gbs, ms in ((0.05, 1.0), (1000.0, 1.0)):
+        n_s, growth = eng.tune_slices(gbs, ms)
+        assert 1 <= n_s <= 12 and 1.25 <= growth <= 4.0
+        eng.q.zero_()
+        out = eng.sweep_from_host(Y_host)
+        assert torch.equal(eng.q, q_ref) and torch.equal(out["z_host"], z_ref.cpu())
 
 
 # ---------------------------------------------------------------------------------------------
