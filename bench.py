@@ -501,7 +501,7 @@ def measure_config(args, torch, dist, hb, ops, synthetic, cfg, scaling, steps, w
     # ---- end-to-end leg: cluster states + host beats in, labels + statistics out ----
     if with_e2e:
         # slice schedule from the two rates measured above (this rank's H2D rate with all ranks copying, the sweep time)
-        out["slices"] = list(eng.tune_slices(h2d_gbs, ms_max)) if h2d_gbs else None
+        out["slices"] = list(eng.tune_slices(h2d_gbs, ms_max, head_start_ms=table_ms)) if h2d_gbs else None
         def e2e_step():
             # the public end-to-end call: table build from (mu, Sigma), pinned host beats in (sliced H2D copies overlapped
             # with scoring), labels and statistics back on the host

@@ -366,19 +366,29 @@ class EStepEngine:
         edges = [0] + [min(N, c * tile) for c in cuts]
         return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
 
-    def tune_slices(self, h2d_gbs, sweep_ms, first_fraction=0.03):
-        """Choose the slice schedule of `sweep_from_host` from two measured rates: the host-to-device rate this rank gets
-        (GB/s, with every rank of the node copying at once) and the time of a device-resident sweep.  A slice may be
-        `growth` times longer than its predecessor only if a beat still copies `growth` times faster than it scores; with
-        eight ranks sharing the host the copy rate halves (55 -> 29 GB/s per rank on the 8 x B200 box) and the 1 : 4 : 16 : 64
-        schedule of a lone rank leaves the last slice waiting for its data (end to end 40.5 ms against 31.4 ms alone)."""
+    def tune_slices(self, h2d_gbs, sweep_ms, head_start_ms=0.0, slice_overhead_ms=0.2, safety=1.15):
+        """Choose the slice schedule of `sweep_from_host` from measured rates: the host-to-device rate this rank gets
+        (GB/s, with every rank of the node copying at once), the time of a device-resident sweep, and the head start the
+        copies have over the scoring (a table build issued before the call).  The candidates (2 to 8 slices, growth 1.25
+        to 4) are played through a two-resource timeline -- a slice is scored when it has arrived and its predecessor is
+        done -- with the copy rate derated by `safety` and `slice_overhead_ms` per slice for the extra launches and grid
+        tails; the fastest wins.  With eight ranks sharing the host the copy rate halves (55 -> 29 GB/s per rank on the
+        8 x B200 box): the 1 : 4 : 16 : 64 schedule of a lone rank then leaves the last slice waiting for its data
+        (end to end 40.5 ms against 31.4 ms alone)."""
         N, L, T = self.N, self.L, self.leads[0].T
-        copy_ms = N * T * L * 8 / (float(h2d_gbs) * 1e9) * 1e3
-        growth = min(4.0, max(1.25, 0.85 * float(sweep_ms) / max(copy_ms, 1e-9)))
-        n = 1
-        while sum(growth ** k for k in range(n)) * first_fraction < 1.0 and n < 12:
-            n += 1
-        self._slice_cfg = (n, growth)
+        copy_ms = safety * N * T * L * 8 / (float(h2d_gbs) * 1e9) * 1e3
+        best = None
+        for n in range(1, 9):
+            for growth in ((1.0,) if n == 1 else (1.25, 1.5, 2.0, 2.5, 3.0, 4.0)):
+                bounds = self.slice_bounds(N, n, growth)
+                t_copy, t_score = 0.0, float(head_start_ms)
+                for n0, n1 in bounds:
+                    f = (n1 - n0) / N
+                    t_copy += copy_ms * f
+                    t_score = max(t_score, t_copy) + float(sweep_ms) * f + slice_overhead_ms
+                if best is None or t_score < best[0] - 1e-9:
+                    best = (t_score, len(bounds), growth)
+        self._slice_cfg = (best[1], best[2])
         return self._slice_cfg
 
     def sweep_from_host(self, Y_host, n_slices=None, growth=None):
