@@ -112,6 +112,7 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
         double* S_new = d.cov_f + (s + 1) * tt;
         // ---------------- Kalman update (GPI.py:104-150) ----------------
         const bool prior = d.first_is_prior && s == 0;
+        const bool have_P = (phases & 1) && !prior;                      // W1 = A Sigma A^T + Gamma survives the update
         if (phases & 1) {
         la_gemv(v0, A, m, T, 0.0, nullptr);                              // v0 = A m  (x_basis_mean)
         const double* P;
@@ -158,8 +159,10 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
         if ((phases & 2) && N > 1) {
             const double* m0 = d.f_star + (int64_t)s * T;
             const double* S0 = d.cov_f + s * tt;
-            la_gemm(W0, A, 0, S0, 0, T, 1.0, 0.0, nullptr, sm);          // A S0
-            la_gemm(W1, W0, 0, A, 1, T, 1.0, 1.0, Gm, sm);               // P = A S0 A^T + Gamma
+            if (!have_P) {                                               // the update of this member started from the same
+                la_gemm(W0, A, 0, S0, 0, T, 1.0, 0.0, nullptr, sm);      // covariance with the same (A, Gamma): its P is
+                la_gemm(W1, W0, 0, A, 1, T, 1.0, 1.0, Gm, sm);           // this P = A S0 A^T + Gamma (two products saved)
+            }
             la_transpose(W5, W1, T);                                     // P^T
             la_gemm(W4, A, 0, S0, 1, T, 1.0, 0.0, nullptr, sm);          // A S0^T
             la_lu_factor(W5, d.piv, T, sm);
@@ -169,9 +172,11 @@ chain_kernel(const hgp_chain_desc* __restrict__ descs, int T) {
             for (int i = threadIdx.x; i < T; i += LA_THREADS) v2[i] = m_new[i] - v2[i];
             __syncthreads();
             la_gemv(d.f_star_sm + (int64_t)s * T, W6, v2, T, 1.0, m0);   // m0 + J (m1 - A m0)
-            la_axpby(W2, 1.0, S_new, -1.0, W1, n);                       // S1 - P
-            la_gemm(W0, W6, 0, W2, 0, T, 1.0, 0.0, nullptr, sm);         // J (S1 - P)
-            la_gemm(d.cov_f_sm + s * tt, W0, 0, W6, 1, T, 1.0, 1.0, S0, sm);   // S0 + J (S1 - P) J^T
+            if (!(phases & 8)) {                                         // the full RTS pass overwrites this covariance
+                la_axpby(W2, 1.0, S_new, -1.0, W1, n);                   // S1 - P
+                la_gemm(W0, W6, 0, W2, 0, T, 1.0, 0.0, nullptr, sm);     // J (S1 - P)
+                la_gemm(d.cov_f_sm + s * tt, W0, 0, W6, 1, T, 1.0, 1.0, S0, sm);   // S0 + J (S1 - P) J^T
+            }
         }
         // ---------------- MNIW step (GPI_model.py:966-1101) ----------------
         if (!(phases & 4)) continue;

@@ -218,7 +218,7 @@ def test_shared_memory_linear_algebra(T):
     assert ops.la_op(14, cu(bad), aux, Li) == 1
 
 
-@pytest.mark.parametrize("pipeline", ["0", "1", "4"])
+@pytest.mark.parametrize("pipeline", ["0", "1", "4", "general"])
 @pytest.mark.parametrize("name", ["offline_rec100_T30_L1", "offline_rec102_T30_L2", "offline_rec100_T90_L1",
                                   "offline_rec100_T30_L1_lim30"])
 def test_chain_replay_vs_reference(golden, name, pipeline, monkeypatch):
@@ -226,7 +226,10 @@ def test_chain_replay_vs_reference(golden, name, pipeline, monkeypatch):
     reference's golden chain dumps: per-step states and the (q, q_lat) it returns.  pipeline: one CTA per chain (0), the
     re-organised member step in one CTA (1), a four-CTA cluster per chain (4, hgp_chain_run_ex)."""
     import hdpgpc_b200 as hb
-    monkeypatch.setenv("HGP_CHAIN_PIPELINE", pipeline)
+    if pipeline == "general":          # the any-T kernel (operands in global memory, pivoted LU): what T > 92 runs
+        monkeypatch.setenv("HGP_CHAIN_V1", "1")
+    else:
+        monkeypatch.setenv("HGP_CHAIN_PIPELINE", pipeline)
     z = golden(name)
     Y = z["data"]
     full = "chain_0_Sigma" in z.files
@@ -287,6 +290,29 @@ def test_batch_chain_keeps_parameters_on_mniw_failure(golden, capsys, pipeline):
     # the internal distribution was kept as well, although only the observation one is broken
     assert torch.equal(gp.internal["m_mean"], torch.eye(T, dtype=torch.float64, device="cuda"))
     assert float(gp.internal["n0"][0]) == float(z["free_deg_MNIV"])
+
+
+def test_chain_beyond_the_shared_memory_path_vs_oracle():
+    """T = 100 (> 92: the general chain kernel, no shared-memory path) on a synthetic cluster of 12 beats: states, parameters
+    and (q, q_lat) against the oracle's chain."""
+    import hdpgpc_b200 as hb
+    rng = np.random.default_rng(5)
+    T, N = 100, 12
+    x = np.arange(T, dtype=np.float64)
+    base = 80.0 * np.exp(-0.5 * ((x - 45.0) / 6.0) ** 2)
+    Y = base[None, :] + rng.standard_normal((N, T)) * 2.0
+    kern = (250.0, 1.2, 0.8)
+    resp = np.ones(N)
+    gp = hb.GPI_model.fresh(x, kern, 0.5, 0.5, free_deg=5)
+    q, ql = gp.full_pass_weighted(None, Y[:, :, None], resp)
+    og = O.OracleGP(x, kern, 0.5, 0.5, free_deg=5)
+    qo, qlo = og.full_pass_weighted(Y, resp, fitted_kernel=kern)
+    assert rel(q, qo) < 1e-7 and rel(ql, qlo) < 1e-7
+    sc = np.max(np.abs(np.stack(og.f_star_sm)))
+    assert np.max(np.abs(gp.f_star_sm.cpu().numpy() - np.stack(og.f_star_sm).reshape(N + 1, T))) < 1e-8 * sc
+    for nm in ["A", "Gamma", "C", "Sigma", "cov_f", "cov_f_sm"]:
+        mine, ref = getattr(gp, nm).cpu().numpy(), np.stack(getattr(og, nm))
+        assert np.max(np.abs(mine - ref)) < 1e-7 * np.max(np.abs(ref)), nm
 
 
 def test_chain_replay_with_device_hyperfit(golden):
